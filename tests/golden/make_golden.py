@@ -1,0 +1,256 @@
+"""Generates the golden fixtures under tests/golden/ by running the LIVE, UNMODIFIED reference
+(/root/reference/src/modules/stm.py, imported through tools/ref_shims.py).
+
+Run in the authoring container only (the reference does not exist on the GPU box):
+
+    python tests/golden/make_golden.py [name ...]
+
+Fixtures (all inputs are stored next to the reference's outputs so tests need nothing else):
+  kat_small.npz        SURVEY Appendix B: K=3, V=6, 2 docs, one E-step + one M-step (STM/ols)
+  estep_K5.npz         state-injected E-steps, D=200 V~370 K=5 (config 1 shape), EM iterations 0 and 2
+  estep_K20.npz        D=96  V~1800 K=20, EM iterations 0 and 1
+  estep_K50.npz        D=64  V~1900 K=50, EM iterations 0 and 1 (PD-repair branch hot in iteration 0)
+  estep_content.npz    A=2 aspects (content=True, kappa_interactions=True), K=8, one E-step + M-step
+  em_c1.npz            config 1 (D=200 V=500 K=5, 1 covariate) full EM to convergence: ELBO trace + final state
+  em_toy_ctm.npz       the reference's own tests/test_integration.py toy pipeline (K=3, CTM, 2 iterations)
+  wiki_corpus.npz      the reference's shipped wiki BoW corpus + X + its shipped iteration-0 ELBOs (K=50, 70)
+
+beta in the state-injected fixtures is rounded to fp32-representable values BEFORE the reference
+runs, so the fp32-beta CUDA path sees bit-identical inputs.
+"""
+import os
+import pickle
+import sys
+import warnings
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(HERE, "..", "..", "tools"))
+import ref_shims  # noqa: E402
+
+warnings.filterwarnings("ignore")
+stm_mod, gd_mod = ref_shims.load_reference()
+REF_ART = "/root/reference/src/artifacts"
+
+
+def to_csr(docs):
+    ptr, ids, cnt = [0], [], []
+    for doc in docs:
+        for w, c in doc:
+            ids.append(int(w))
+            cnt.append(float(c))
+        ptr.append(len(ids))
+    return np.array(ptr, np.int64), np.array(ids, np.int32), np.array(cnt, np.float64)
+
+
+def instrumented_estep(model):
+    """Run the reference E_step while recording per-document bound and BFGS diagnostics through
+    wrappers around its own methods (the reference code itself is untouched)."""
+    rec = dict(bound=[], status=[], nit=[], nfev=[], njev=[])
+    orig_lb, orig_opt = model.lower_bound, model.optimize_eta
+
+    def lb(*a, **k):
+        v = orig_lb(*a, **k)
+        rec["bound"].append(float(v))
+        return v
+
+    def opt(*a, **k):
+        r = orig_opt(*a, **k)
+        rec["status"].append(r.status)
+        rec["nit"].append(r.nit)
+        rec["nfev"].append(r.nfev)
+        rec["njev"].append(r.njev)
+        return r
+
+    model.lower_bound, model.optimize_eta = lb, opt
+    try:
+        beta_ss, sigma_ss = model.E_step()
+    finally:
+        model.lower_bound, model.optimize_eta = orig_lb, orig_opt
+    return beta_ss, sigma_ss, {k: np.array(v) for k, v in rec.items()}
+
+
+def snapshot_estep(model, prefix, out, round_beta=True, keep_m_beta=True):
+    """Records inputs, runs the reference E-step + M-step, records outputs under `prefix`."""
+    if round_beta:
+        model.beta = np.asarray(model.beta, dtype=np.float32).astype(np.float64)
+    # fp32-representable by construction when round_beta: store compactly
+    out[prefix + "beta"] = np.array(model.beta, dtype=np.float32 if round_beta else np.float64)
+    out[prefix + "mu"] = np.array(model.mu)
+    out[prefix + "sigma"] = np.array(model.sigma)
+    out[prefix + "eta0"] = np.array(model.eta)
+    beta_ss, sigma_ss, rec = instrumented_estep(model)
+    out[prefix + "siginv"] = np.array(model.siginv)
+    out[prefix + "sigmaentropy"] = np.float64(model.sigmaentropy)
+    out[prefix + "eta"] = np.array(model.eta)
+    out[prefix + "theta"] = np.array(model.theta)
+    out[prefix + "bound"] = np.float64(model.bound)
+    out[prefix + "beta_ss"] = np.array(beta_ss)
+    out[prefix + "sigma_ss"] = np.array(sigma_ss)
+    out[prefix + "doc_bound"] = rec["bound"]
+    out[prefix + "status"] = rec["status"].astype(np.int32)
+    out[prefix + "nit"] = rec["nit"].astype(np.int32)
+    model.M_step(beta_ss, sigma_ss)
+    if keep_m_beta:
+        out[prefix + "m_beta"] = np.array(model.beta)
+    out[prefix + "m_mu"] = np.array(model.mu)
+    out[prefix + "m_sigma"] = np.array(model.sigma)
+    if getattr(model, "gamma", None) is not None:
+        out[prefix + "m_gamma"] = np.array(model.gamma)
+
+
+def synthetic(K, V, D, n_words, seed, level=1):
+    np.random.seed(seed)
+    corpus = gd_mod.CorpusCreation(n_topics=K, n_docs=D, n_words=n_words, V=V, level=level, dgp="STM")
+    corpus.generate_documents(remove_terms=False)
+    return corpus
+
+
+def make_model(docs, dictionary, K, X, iters, model_type="STM", content=False, interactions=False,
+               A=None, beta_index=None, thr=1e-5):
+    return stm_mod.STM(documents=docs, dictionary=dictionary, content=content, K=K, X=X,
+                       kappa_interactions=interactions, max_em_iter=iters, sigma_prior=0,
+                       convergence_threshold=thr, init_type="random", model_type=model_type,
+                       mode="ols", A=A, beta_index=beta_index)
+
+
+def save(name, out):
+    path = os.path.join(HERE, name)
+    np.savez_compressed(path, **out)
+    print(f"wrote {path} ({os.path.getsize(path) / 1024:.0f} KiB)")
+
+
+# ------------------------------------------------------------------------------------------------
+
+def kat_small():
+    docs = [[(0, 3), (2, 1), (3, 2), (5, 4)], [(1, 2), (2, 2), (4, 1)]]
+    X = np.array([[0], [1]])
+    m = make_model(docs, {i: str(i) for i in range(6)}, 3, X, 2)
+    B = np.array([[6, 1, 1, 1, 2, 1], [1, 5, 2, 1, 1, 2], [1, 1, 1, 4, 1, 4]], float)
+    m.beta = B / B.sum(1, keepdims=True)
+    m.mu = np.array([[0.2, -0.1], [0.0, 0.3]])
+    m.sigma = np.array([[1.5, 0.4], [0.4, 0.8]])
+    m.eta = np.array([[0.1, -0.2], [0.0, 0.0]])
+    out = {}
+    out["doc_ptr"], out["word_id"], out["count"] = to_csr(docs)
+    out["X"] = X
+    out["K"], out["V"] = np.int64(3), np.int64(6)
+    snapshot_estep(m, "it0_", out, round_beta=False)
+    save("kat_small.npz", out)
+
+
+def estep_fixture(name, K, V, D, seed, iters_to_record, n_iters, keep_m_beta=True):
+    corpus = synthetic(K, V, D, 150, seed)
+    m = make_model(corpus.documents, corpus.dictionary, K, corpus.metadata, n_iters)
+    out = {}
+    out["doc_ptr"], out["word_id"], out["count"] = to_csr(corpus.documents)
+    out["X"] = np.array(corpus.metadata)
+    out["K"], out["V"] = np.int64(K), np.int64(m.V)
+    for it in range(n_iters):
+        if it in iters_to_record:
+            snapshot_estep(m, f"it{it}_", out, keep_m_beta=keep_m_beta)
+        else:
+            bss, sss = m.E_step()
+            m.M_step(bss, sss)
+    out["recorded"] = np.array(sorted(iters_to_record), np.int64)
+    save(name, out)
+
+
+def estep_content():
+    K, V, D, A = 8, 400, 48, 2
+    corpus = synthetic(K, V, D, 120, 7)
+    aspect = (np.arange(D) % A).astype(np.int32)
+    m = make_model(corpus.documents, corpus.dictionary, K, corpus.metadata, 2, content=True,
+                   interactions=True, A=A, beta_index=aspect)
+    # give the two aspects different betas so the aspect gather matters
+    rng = np.random.default_rng(3)
+    b = m.beta * rng.uniform(0.5, 1.5, size=m.beta.shape)
+    m.beta = b / b.sum(axis=2, keepdims=True)
+    out = {}
+    out["doc_ptr"], out["word_id"], out["count"] = to_csr(corpus.documents)
+    out["X"] = np.array(corpus.metadata)
+    out["aspect"] = aspect
+    out["K"], out["V"], out["A"] = np.int64(K), np.int64(m.V), np.int64(A)
+    snapshot_estep(m, "it0_", out)
+    save("estep_content.npz", out)
+
+
+def em_c1():
+    """BASELINE.json configs[0]: D=200 V=500 K=5, 1 prevalence covariate, EM to convergence."""
+    K, V, D = 5, 500, 200
+    corpus = synthetic(K, V, D, 150, 12345)
+    m = make_model(corpus.documents, corpus.dictionary, K, corpus.metadata, 100)
+    out = {}
+    out["doc_ptr"], out["word_id"], out["count"] = to_csr(corpus.documents)
+    out["X"] = np.array(corpus.metadata)
+    out["K"], out["V"] = np.int64(K), np.int64(m.V)
+    out["beta0"] = np.array(m.beta)
+    m.expectation_maximization(saving=False)
+    out["bounds"] = np.array(m.last_bounds)
+    for k in ("beta", "theta", "eta", "mu", "sigma", "gamma"):
+        out["final_" + k] = np.array(getattr(m, k))
+    print("em_c1: iterations", len(m.last_bounds), "final bound", m.last_bounds[-1])
+    save("em_c1.npz", out)
+
+
+def em_toy_ctm():
+    """tests/test_integration.py:14-68 of the reference, verbatim parameters."""
+    np.random.seed(42)
+    K, V, N, n_words, level = 3, 200, 50, 50, 1
+    gamma = np.random.multivariate_normal(np.random.standard_normal(level),
+                                          np.diag(np.full(level, 0.001)), K - 1)
+    corpus = gd_mod.CorpusCreation(n_topics=K, n_docs=N, n_words=n_words, V=V, level=level,
+                                   dgp="STM", gamma=gamma)
+    corpus.generate_documents(remove_terms=True)
+    corpus.split_corpus(proportion=0.8)
+    docs = corpus.train_docs
+    np.random.seed(42)
+    m = make_model(docs, corpus.dictionary, K, corpus.metadata[:len(docs)], 2, model_type="CTM")
+    out = {}
+    out["doc_ptr"], out["word_id"], out["count"] = to_csr(docs)
+    out["X"] = np.array(corpus.metadata[:len(docs)])
+    out["K"], out["V"] = np.int64(K), np.int64(m.V)
+    out["beta0"] = np.array(m.beta)
+    m.expectation_maximization(saving=False)
+    out["bounds"] = np.array(m.last_bounds)
+    for k in ("beta", "theta", "eta", "mu", "sigma"):
+        out["final_" + k] = np.array(getattr(m, k))
+    from modules.heldout import eval_heldout
+    out["heldout_ll"] = np.float64(eval_heldout(corpus.test_2_docs, m.theta, m.beta))
+    h_ptr, h_ids, h_cnt = to_csr(corpus.test_2_docs)
+    out["heldout_doc_ptr"], out["heldout_word_id"], out["heldout_count"] = h_ptr, h_ids, h_cnt
+    save("em_toy_ctm.npz", out)
+
+
+def wiki_corpus():
+    """The reference's shipped corpus + its shipped known-answer ELBOs."""
+    import scipy.io
+    mm = scipy.io.mmread(os.path.join(REF_ART, "wiki_data", "BoW_corpus.mm")).tocsr()
+    mm.sort_indices()
+    out = dict(doc_ptr=mm.indptr.astype(np.int64), word_id=mm.indices.astype(np.int32),
+               count=mm.data.astype(np.int16), V=np.int64(mm.shape[1]))
+    assert np.array_equal(out["count"].astype(np.float64), mm.data)
+    for K in (50, 70):
+        d = os.path.join(REF_ART, "reference_model", str(K))
+        out[f"X_{K}"] = np.load(os.path.join(d, "X.npy"), allow_pickle=True)
+        with open(os.path.join(d, "lower_bound.pickle"), "rb") as fh:
+            out[f"shipped_bounds_{K}"] = np.array(pickle.load(fh), dtype=np.float64)
+    save("wiki_corpus.npz", out)
+
+
+ALL = dict(
+    kat_small=kat_small,
+    estep_K5=lambda: estep_fixture("estep_K5.npz", 5, 500, 200, 12345, {0, 2}, 3),
+    estep_K20=lambda: estep_fixture("estep_K20.npz", 20, 2000, 96, 1, {0, 1}, 2, keep_m_beta=False),
+    estep_K50=lambda: estep_fixture("estep_K50.npz", 50, 2000, 64, 2, {0, 1}, 2, keep_m_beta=False),
+    estep_content=estep_content,
+    em_c1=em_c1,
+    em_toy_ctm=em_toy_ctm,
+    wiki_corpus=wiki_corpus,
+)
+
+if __name__ == "__main__":
+    names = sys.argv[1:] or list(ALL)
+    for n in names:
+        ALL[n]()
