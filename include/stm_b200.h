@@ -1,0 +1,133 @@
+/*
+ * stm_b200.h — C ABI of the B200-native STM variational-EM core (libstm_b200.so).
+ *
+ * The reference (mkrcke/strutopy) has no FFI: the hot path sits behind the Python class
+ * `STM` (/root/reference/src/modules/stm.py:310).  Each entry point below cites the reference
+ * method it replaces; `strutopy_b200/stm.py` is the drop-in `STM` front that binds them through
+ * ctypes (INTEGRATION.md shows the stub a maintainer would add to the reference itself).
+ *
+ * Conventions
+ *   - plain C types only; every function returns 0 on success or a negative STM_ERR_* code;
+ *     stm_last_error() gives the message.  No exceptions cross the ABI.
+ *   - one context per GPU; calls on a context are serialised by the caller.
+ *   - "dev" pointers are device pointers OWNED BY THE CALLER (the Python front allocates them as
+ *     torch tensors); "host" pointers are host memory (pinned memory makes copies asynchronous).
+ *   - device-pointer entry points are asynchronous on `stream` (a cudaStream_t passed as void*);
+ *     host-pointer entry points block until their outputs are valid.
+ *   - matrices are row-major.  K1 = K-1.  TS = stm_beta_stride(K): word-major beta row stride.
+ */
+#ifndef STM_B200_H
+#define STM_B200_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct stm_ctx stm_ctx;
+
+enum {
+    STM_OK = 0,
+    STM_ERR_INVALID = -1,      /* bad argument (reference: ValueError / AssertionError) */
+    STM_ERR_CUDA = -2,         /* CUDA / cuBLAS / cuSOLVER failure */
+    STM_ERR_NOT_PD = -3,       /* Sigma not positive definite (reference: stm.py:503-510 raises) */
+    STM_ERR_UNSUPPORTED = -4,  /* e.g. non-diagonal siginv, K > 128, document too long for shared memory */
+    STM_ERR_NO_CORPUS = -5
+};
+
+/* model type / regression mode of update_mu (stm.py:636-711) */
+enum { STM_MODEL_STM = 0, STM_MODEL_CTM = 1 };
+
+/* ---- lifecycle --------------------------------------------------------------------------------- */
+
+/* STM.__init__ (stm.py:311-399) shape part: K topics, V vocabulary, A content-covariate levels
+ * (1 when no content model).  Selects `device`, creates cuBLAS/cuSOLVER handles. */
+int stm_create(int device, int K, int V, int A, stm_ctx** out);
+void stm_destroy(stm_ctx* ctx);
+/* message of the last failure on ctx (ctx may be NULL for a failed stm_create) */
+const char* stm_last_error(const stm_ctx* ctx);
+/* word-major beta row stride in elements: smallest multiple of 4 >= K whose quarter is odd */
+int stm_beta_stride(int K);
+/* number of E-step kernel launches issued so far on this context (bench.py's gpu_launches) */
+int64_t stm_launch_count(const stm_ctx* ctx);
+
+/* ---- corpus ------------------------------------------------------------------------------------ */
+
+/* `self.documents` (stm.py:331-332, 366) as CSR, uploaded once per fit: doc_ptr[D+1], word_id[nnz]
+ * (unique within a document, 0 <= id < V), count[nnz]; aspect[D] = `beta_index` (stm.py:378, 528)
+ * or NULL.  Host pointers.  Builds the document length classes used to size shared memory. */
+int stm_set_corpus(stm_ctx* ctx, int64_t D, const int64_t* doc_ptr, const int32_t* word_id,
+                   const float* count, const int32_t* aspect);
+
+/* ---- packed sufficient-statistics buffer (the one all-reduced across GPUs) ---------------------
+ * fp64, layout for p prevalence covariates:
+ *   [0] beta_ss_t  A*V*TS   word-major phi sums        (stm.py:515, 585-588)
+ *   [1] sigma_ss   K1*K1    sum of nu                   (stm.py:514, 582)
+ *   [2] bound      1        sum of per-document bounds  (stm.py:592)
+ *   [3] n_docs     1
+ *   [4] sum_eta    K1       [5] sum_x p      [6] xtx p*p      [7] xte p*K1     [8] ete K1*K1
+ * offsets[10]: start of each of the 9 segments, offsets[9] = total length (doubles). */
+int stm_stats_layout(const stm_ctx* ctx, int p, int64_t* offsets);
+
+/* ---- E-step ------------------------------------------------------------------------------------ */
+
+/* E-step prologue (stm.py:497-501) on device: Cholesky of sigma (cuSOLVER potrf) ->
+ * prior_dev[K1+1] = { diag(siginv)[K1], sigmaentropy }.  info_dev (int, device) receives the
+ * potrf info (0 = ok, >0 = not PD).  sigma_dev is K1*K1 and is not modified. */
+int stm_prologue(stm_ctx* ctx, const double* sigma_dev, double* prior_dev, int* info_dev, void* stream);
+
+/* STM.E_step document loop (stm.py:519-593) — ONE kernel launch per document length class.
+ *   beta_t_dev   float [A][V][TS]   word-major beta (padding columns zero)
+ *   mu_dev       double [D][K1]
+ *   prior_dev    double [K1+1]      from stm_prologue
+ *   eta_dev      double [D][K1]     in: warm start (stm.py:539)  out: optimum (stm.py:546)
+ *   theta_dev    double [D][K]      out (stm.py:547-549)
+ *   stats_dev    packed buffer; segments 0-3 are (re)written
+ *   doc_bound_dev double [D]; doc_info_dev int32 [D] (status | nit<<4 | repair<<24);
+ *   doc_nfev_dev int32 [D]          per-document diagnostics (always written) */
+int stm_estep(stm_ctx* ctx, const float* beta_t_dev, const double* mu_dev, const double* prior_dev,
+              double* eta_dev, double* theta_dev, double* stats_dev, double* doc_bound_dev,
+              int32_t* doc_info_dev, int32_t* doc_nfev_dev, void* stream);
+
+/* ---- M-step ------------------------------------------------------------------------------------ */
+
+/* local moments of (eta, X) for update_mu/update_sigma (stm.py:636-728) into stats segments 4-8
+ * (cuBLAS).  x_dev: double [D][p] design matrix (already one-hot encoded where the reference
+ * would, stm.py:669-671); p may be 0 for CTM. */
+int stm_moments(stm_ctx* ctx, const double* eta_dev, const double* x_dev, int p, double* stats_dev,
+                void* stream);
+
+/* M_step (stm.py:622-634) from the (all-reduced) statistics:
+ *   update_mu   (stm.py:636-711): centred min-norm OLS (sklearn LinearRegression semantics,
+ *               cond=1e-6), intercept dropped: gamma_t_dev [p][K1], mu_dev[D][K1] = X gamma'
+ *               (CTM: mu = column mean of eta)
+ *   update_sigma(stm.py:713-728): sigma_dev [K1][K1], shrunk by sigprior
+ *   update_beta (stm.py:739-745): beta_t_dev float [A][V][TS] (A>1: the reference normalises over
+ *               the topic axis, kept), optionally beta64_t_dev double [A][V][TS] (may be NULL)
+ * n_total = global number of documents (stats[3] after the all-reduce). */
+int stm_mstep(stm_ctx* ctx, const double* stats_dev, const double* x_dev, int p, int model,
+              double sigprior, double* gamma_t_dev, double* mu_dev, double* sigma_dev,
+              float* beta_t_dev, double* beta64_t_dev, void* stream);
+
+/* ---- layout helpers (device) ------------------------------------------------------------------- */
+
+/* reference-layout beta double [A][K][V] (device) -> word-major float [A][V][TS] (device) */
+int stm_beta_to_wordmajor(stm_ctx* ctx, const double* beta_kv_dev, float* beta_t_dev, void* stream);
+/* word-major double [A][V][TS] (device) -> reference layout double [A][K][V] (device) */
+int stm_wordmajor_to_kv(stm_ctx* ctx, const double* src_t_dev, double* dst_kv_dev, void* stream);
+
+/* ---- host-buffer entry point: what a reference-side binding calls ------------------------------
+ * One full E_step() with the reference's own argument layout, HOST pointers, fp64:
+ *   beta [A][K][V], mu [D][K1], siginv [K1][K1] (must be diagonal, as stm.py:501 produces),
+ *   sigmaentropy, eta [D][K1] in/out, theta [D][K] out, beta_ss [A][K][V] out, sigma_ss [K1][K1]
+ *   out, bound out; doc_bound/doc_status/doc_nit/doc_repair [D] may be NULL.
+ * Copies in, runs stm_estep, copies out; blocks until done. */
+int stm_estep_host(stm_ctx* ctx, const double* beta, const double* mu, const double* siginv,
+                   double sigmaentropy, double* eta, double* theta, double* beta_ss,
+                   double* sigma_ss, double* bound, double* doc_bound, int32_t* doc_status,
+                   int32_t* doc_nit, int32_t* doc_repair);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

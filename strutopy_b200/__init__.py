@@ -1,0 +1,9 @@
+"""strutopy_b200 — B200-native variational-EM core for the Structural Topic Model, behind the
+`STM(...)` / `expectation_maximization()` / `E_step()` / `M_step()` surface of mkrcke/strutopy
+(/root/reference/src/modules/stm.py:310).  Hand-written CUDA for sm_100a through a C ABI
+(include/stm_b200.h); no CPU fallback."""
+from . import _lib  # noqa: F401
+from .corpus import pack_corpus  # noqa: F401
+from .stm import STM  # noqa: F401
+
+__all__ = ["STM", "pack_corpus"]

@@ -1,0 +1,28 @@
+// estep_inst.cu — instantiates stm::estep_kernel<STM_KPL, J> for J in {2,4,5,8}; compiled once per
+// STM_KPL in {1,2,3,4} (K <= 32*STM_KPL) so the instantiations build in parallel.
+#include "estep_kernel.cuh"
+
+#ifndef STM_KPL
+#error "compile with -DSTM_KPL=1..4"
+#endif
+#define STM_CAT2(a, b) a##b
+#define STM_CAT(a, b) STM_CAT2(a, b)
+
+cudaError_t STM_CAT(stm_launch_kpl, STM_KPL)(const stm::EstepParams& P, int J, int grid, int block,
+                                             size_t smem, cudaStream_t st) {
+#define STM_LAUNCH(JJ)                                                                                \
+    {                                                                                                 \
+        cudaError_t e = cudaFuncSetAttribute(stm::estep_kernel<STM_KPL, JJ>,                          \
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+        if (e != cudaSuccess) return e;                                                               \
+        stm::estep_kernel<STM_KPL, JJ><<<grid, block, smem, st>>>(P);                                 \
+        return cudaGetLastError();                                                                    \
+    }
+    switch (J) {
+        case 2: STM_LAUNCH(2)
+        case 4: STM_LAUNCH(4)
+        case 5: STM_LAUNCH(5)
+        default: STM_LAUNCH(8)
+    }
+#undef STM_LAUNCH
+}

@@ -1,0 +1,993 @@
+// estep_kernel.cuh — the STM E-step as ONE sm_100a kernel: per-document Laplace-variational inference.
+//
+// Replaces the document loop of the reference, /root/reference/src/modules/stm.py:519-590
+// (get_beta :599, optimize_eta :917 -> scipy BFGS, hessian :986, make_pd :964, decompose_hessian
+// :1031, lower_bound :1068, optimize_nu :1052, update_z :1103, accumulation :582-590).
+//
+// Mapping:
+//   * one WARP per document, persistent warps pulling document indices from an atomic queue;
+//     control flow (SciPy's BFGS / dcsrch / zoom state machine) is warp-uniform, so different
+//     documents diverge across warps for free;
+//   * the document's beta rows (fp32, word-major [V][TS]) are gathered ONCE into shared memory by
+//     TMA bulk copies (cp.async.bulk, one 16B-aligned row per word, completion on an mbarrier);
+//   * every objective evaluation is a (K x n_d) contraction out of shared memory with fp64
+//     accumulation, warp-shuffle reductions, fp64 line-search scalars;
+//   * K-vectors (eta, p, g, ...) live in registers, lane l owning k = l, l+32, ...;
+//   * the dense BFGS inverse-Hessian lives in a per-warp L2-resident scratch (touched once per
+//     accepted step); the Laplace Hessian is accumulated in register blocks, then factorised in the
+//     shared memory the beta tile occupied;
+//   * phi is scattered into beta_ss with fp64 reductions (red.global.add.f64), nu into replicated
+//     sigma_ss accumulators.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <math.h>
+
+namespace stm {
+
+struct EstepParams {
+    // corpus (CSR), resident in HBM for the whole fit
+    const long long* doc_ptr;   // [D+1]
+    const int* word_id;         // [nnz]
+    const float* count;         // [nnz]
+    const int* aspect;          // [D] or nullptr
+    // work list of this launch (documents of one length class)
+    const int* docs;            // [n_docs] document indices
+    int n_docs;
+    unsigned int* queue;        // atomic work counter (zeroed before launch)
+    // model
+    int K, V, A;
+    int TS;                     // beta row stride in floats (multiple of 4, TS/4 odd)
+    const float* beta_t;        // [A][V][TS] word-major beta
+    const double* mu;           // [D][K-1]
+    const double* prior;        // [K-1] diagonal of siginv (stm.py:501 makes it diagonal), then sigmaentropy
+    // per-document state / outputs
+    double* eta;                // [D][K-1] in: warm start, out: result
+    double* theta;              // [D][K]
+    double* doc_bound;          // [D]
+    int* doc_info;              // [D] status | nit<<4 | repair<<24   (nit clipped to 20 bits)
+    int* doc_nfev;              // [D] objective evaluations actually performed
+    // sufficient statistics
+    double* beta_ss_t;          // [A][V][TS] fp64, accumulated
+    double* sigma_ss_rep;       // [n_rep][(K-1)*(K-1)] replicated accumulators (lower triangle used)
+    int n_rep;
+    // per-warp scratch in HBM/L2: 2 * HS*K1 doubles (BFGS inverse Hessian, Laplace Hessian)
+    double* scratch;
+    long long scratch_stride;   // doubles per warp
+    // shared memory geometry
+    int n_cap;                  // tile rows (words) per warp
+    int smem_per_warp;          // bytes
+};
+
+#define STM_FULL 0xffffffffu
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(STM_FULL, v, o);
+    return v;
+}
+__device__ __forceinline__ double nanmax(double a, double b) {
+    return (isnan(a) || isnan(b)) ? nan("") : fmax(a, b);
+}
+__device__ __forceinline__ double warp_max(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = nanmax(v, __shfl_xor_sync(STM_FULL, v, o));
+    return v;
+}
+
+// Python / NumPy comparison semantics used by SciPy's line searches (see oracle/stm_oracle.c)
+__device__ __forceinline__ double py_max3(double a, double b, double c) {
+    double m = a;
+    if (b > m) m = b;
+    if (c > m) m = c;
+    return m;
+}
+__device__ __forceinline__ double py_max2(double a, double b) { return (b > a) ? b : a; }
+__device__ __forceinline__ double py_min2(double a, double b) { return (b < a) ? b : a; }
+__device__ __forceinline__ double np_clip(double x, double lo, double hi) {
+    if (isnan(x)) return x;
+    double t = (x < lo) ? lo : x;
+    return (t > hi) ? hi : t;
+}
+__device__ __forceinline__ double np_sign(double x) {
+    if (isnan(x)) return x;
+    return (x > 0.0) ? 1.0 : ((x < 0.0) ? -1.0 : 0.0);
+}
+
+// MINPACK-2 dcstep — scipy/optimize/_dcsrch.py:502-728
+static __device__ __noinline__ void dcstep(double& stx, double& fx, double& dx, double& sty, double& fy,
+                                    double& dy, double& stp, double fp, double dp, int& brackt,
+                                    double stpmin, double stpmax) {
+    const double sgnd = np_sign(dp) * np_sign(dx);
+    double theta, s, gamma, p, q, r, stpc, stpq, stpf;
+    if (fp > fx) {
+        theta = 3.0 * (fx - fp) / (stp - stx) + dx + dp;
+        s = py_max3(fabs(theta), fabs(dx), fabs(dp));
+        gamma = s * sqrt((theta / s) * (theta / s) - (dx / s) * (dp / s));
+        if (stp < stx) gamma = -gamma;
+        p = (gamma - dx) + theta;
+        q = ((gamma - dx) + gamma) + dp;
+        r = p / q;
+        stpc = stx + r * (stp - stx);
+        stpq = stx + ((dx / ((fx - fp) / (stp - stx) + dx)) / 2.0) * (stp - stx);
+        if (fabs(stpc - stx) <= fabs(stpq - stx)) stpf = stpc;
+        else stpf = stpc + (stpq - stpc) / 2.0;
+        brackt = 1;
+    } else if (sgnd < 0.0) {
+        theta = 3.0 * (fx - fp) / (stp - stx) + dx + dp;
+        s = py_max3(fabs(theta), fabs(dx), fabs(dp));
+        gamma = s * sqrt((theta / s) * (theta / s) - (dx / s) * (dp / s));
+        if (stp > stx) gamma = -gamma;
+        p = (gamma - dp) + theta;
+        q = ((gamma - dp) + gamma) + dx;
+        r = p / q;
+        stpc = stp + r * (stx - stp);
+        stpq = stp + (dp / (dp - dx)) * (stx - stp);
+        if (fabs(stpc - stp) > fabs(stpq - stp)) stpf = stpc;
+        else stpf = stpq;
+        brackt = 1;
+    } else if (fabs(dp) < fabs(dx)) {
+        theta = 3.0 * (fx - fp) / (stp - stx) + dx + dp;
+        s = py_max3(fabs(theta), fabs(dx), fabs(dp));
+        gamma = s * sqrt(py_max2(0.0, (theta / s) * (theta / s) - (dx / s) * (dp / s)));
+        if (stp > stx) gamma = -gamma;
+        p = (gamma - dp) + theta;
+        q = (gamma + (dx - dp)) + gamma;
+        r = p / q;
+        if (r < 0.0 && gamma != 0.0) stpc = stp + r * (stx - stp);
+        else if (stp > stx) stpc = stpmax;
+        else stpc = stpmin;
+        stpq = stp + (dp / (dp - dx)) * (stx - stp);
+        if (brackt) {
+            if (fabs(stpc - stp) < fabs(stpq - stp)) stpf = stpc;
+            else stpf = stpq;
+            if (stp > stx) stpf = py_min2(stp + 0.66 * (sty - stp), stpf);
+            else stpf = py_max2(stp + 0.66 * (sty - stp), stpf);
+        } else {
+            if (fabs(stpc - stp) > fabs(stpq - stp)) stpf = stpc;
+            else stpf = stpq;
+            stpf = np_clip(stpf, stpmin, stpmax);
+        }
+    } else {
+        if (brackt) {
+            theta = 3.0 * (fp - fy) / (sty - stp) + dy + dp;
+            s = py_max3(fabs(theta), fabs(dy), fabs(dp));
+            gamma = s * sqrt((theta / s) * (theta / s) - (dy / s) * (dp / s));
+            if (stp > sty) gamma = -gamma;
+            p = (gamma - dp) + theta;
+            q = ((gamma - dp) + gamma) + dy;
+            r = p / q;
+            stpc = stp + r * (sty - stp);
+            stpf = stpc;
+        } else if (stp > stx) stpf = stpmax;
+        else stpf = stpmin;
+    }
+    if (fp > fx) {
+        sty = stp; fy = fp; dy = dp;
+    } else {
+        if (sgnd < 0.0) { sty = stx; fy = fx; dy = dx; }
+        stx = stp; fx = fp; dx = dp;
+    }
+    stp = stpf;
+}
+
+// scipy/optimize/_linesearch.py:491-543; NaN stands for None
+static __device__ __noinline__ double cubicmin(double a, double fa, double fpa, double b, double fb,
+                                        double c, double fc) {
+    const double C = fpa, db = b - a, dc = c - a;
+    const double denom = (db * dc) * (db * dc) * (db - dc);
+    const double d00 = dc * dc, d01 = -(db * db), d10 = -(dc * dc * dc), d11 = db * db * db;
+    const double v0 = fb - fa - C * db, v1 = fc - fa - C * dc;
+    double A = __dadd_rn(__dmul_rn(d00, v0), __dmul_rn(d01, v1));
+    double B = __dadd_rn(__dmul_rn(d10, v0), __dmul_rn(d11, v1));
+    if (denom == 0.0) return nan("");
+    A /= denom;
+    B /= denom;
+    const double radical = __dadd_rn(__dmul_rn(B, B), -__dmul_rn(3.0 * A, C));
+    if (radical < 0.0 || A == 0.0) return nan("");
+    const double xmin = a + (-B + sqrt(radical)) / (3.0 * A);
+    if (!isfinite(xmin)) return nan("");
+    return xmin;
+}
+static __device__ __noinline__ double quadmin(double a, double fa, double fpa, double b, double fb) {
+    const double D = fa, C = fpa, db = b - a * 1.0;
+    if (db * db == 0.0) return nan("");
+    const double B = __dadd_rn(__dadd_rn(fb, -D), -__dmul_rn(C, db)) / (db * db);
+    if (2.0 * B == 0.0) return nan("");
+    const double xmin = a - C / (2.0 * B);
+    if (!isfinite(xmin)) return nan("");
+    return xmin;
+}
+
+// ---- TMA bulk copy + mbarrier (PTX) -----------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+    return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "LAB_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+        "@P1 bra DONE;\n"
+        "bra LAB_WAIT;\n"
+        "DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void tma_row_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+            smem_u32(dst)),
+        "l"(src), "r"(bytes), "r"(smem_u32(bar))
+        : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() {
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void red_add_f64(double* addr, double v) {
+    asm volatile("red.global.add.f64 [%0], %1;" ::"l"(addr), "d"(v) : "memory");
+}
+
+// status / repair codes mirror oracle/stm_oracle.h
+enum { LS_INIT = 0, LS_W1 = 1, LS_W2 = 2, LS_ZOOM = 3 };
+
+template <int KPL, int J>
+__global__ void __launch_bounds__(256, 1) estep_kernel(const EstepParams P) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    const int K = P.K, K1 = K - 1, TS = P.TS;
+    constexpr int KV = KPL * 32;
+    constexpr int KVS = KV + 8;  // padded stride of the shared K-vectors (TS <= KV+4, block reads <= KV+6)
+    const int HS = K1 | 1;  // odd row stride (doubles) of the dense (K-1)x(K-1) matrices in smem
+
+    // ---- per-warp shared memory carve-up -----------------------------------------------------
+    unsigned char* base = smem_raw + (size_t)warp * P.smem_per_warp;
+    size_t tile_bytes = (size_t)P.n_cap * TS * 4;
+    const size_t h_bytes = (size_t)K1 * HS * 8;
+    if (h_bytes > tile_bytes) tile_bytes = h_bytes;
+    tile_bytes = (tile_bytes + 127) & ~(size_t)127;
+    float* tile = reinterpret_cast<float*>(base);
+    double* Hm = reinterpret_cast<double*>(base);  // aliases the tile once it is dead
+    double* wv = reinterpret_cast<double*>(base + tile_bytes);            // [n_cap] per-word fp64
+    double* vec = wv + P.n_cap;                                           // [4][KVS]
+    float* cw = reinterpret_cast<float*>(vec + 4 * KVS);                  // [n_cap] counts
+    int* wid = reinterpret_cast<int*>(cw + P.n_cap);                      // [n_cap]
+    uint64_t* mbar = reinterpret_cast<uint64_t*>(wid + P.n_cap);
+    double* v0 = vec;            // e / broadcast scratch
+    double* v1 = vec + KVS;
+    double* v2 = vec + 2 * KVS;
+    double* v3 = vec + 3 * KVS;
+    for (int i = lane; i < 4 * KVS; i += 32) vec[i] = 0.0;  // pads stay zero for the whole kernel
+
+    if (lane == 0) mbar_init(mbar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    __syncwarp();
+    uint32_t parity = 0;
+
+    const int gwarp = blockIdx.x * (blockDim.x >> 5) + warp;
+    double* Hk = P.scratch + (size_t)gwarp * P.scratch_stride;  // BFGS inverse Hessian [K1][K1]
+    double* Hg = Hk + (size_t)K1 * K1;                          // Laplace Hessian bounce [K1][K1]
+    double* sig_acc = P.sigma_ss_rep + (size_t)(gwarp % P.n_rep) * K1 * K1;
+
+    // diagonal of siginv, lane-distributed
+    double Sd[KPL];
+#pragma unroll
+    for (int i = 0; i < KPL; ++i) {
+        const int k = lane + 32 * i;
+        Sd[i] = (k < K1) ? P.prior[k] : 0.0;
+    }
+    const double sigmaentropy = P.prior[K1];
+
+    for (;;) {
+        int qi = 0;
+        if (lane == 0) qi = (int)atomicAdd(P.queue, 1u);
+        qi = __shfl_sync(STM_FULL, qi, 0);
+        if (qi >= P.n_docs) break;
+        const int d = P.docs[qi];
+        const long long p0 = P.doc_ptr[d];
+        const int n = (int)(P.doc_ptr[d + 1] - p0);
+        const int asp = P.aspect ? P.aspect[d] : 0;
+        const float* beta_a = P.beta_t + (size_t)asp * P.V * TS;
+
+        // ---- stage ids / counts, then TMA-gather the beta rows --------------------------------
+        fence_proxy_async();  // previous document's generic writes to this smem precede async writes
+        __syncwarp();
+        if (lane == 0) mbar_expect_tx(mbar, (uint32_t)(n * TS * 4));
+        __syncwarp();
+        double nsum_l = 0.0;
+        for (int v = lane; v < n; v += 32) {
+            const int w = P.word_id[p0 + v];
+            const float c = P.count[p0 + v];
+            wid[v] = w;
+            cw[v] = c;
+            nsum_l += (double)c;
+            tma_row_g2s(tile + (size_t)v * TS, beta_a + (size_t)w * TS, (uint32_t)(TS * 4), mbar);
+        }
+        const double Nsum = warp_sum(nsum_l);           // np.sum(word_count)       stm.py:955
+        const double Nint = (double)(long long)Nsum;    // int(np.sum(word_count))  stm.py:933
+
+        double x[KPL], mu[KPL], p[KPL], g[KPL], gt[KPL], xt[KPL], a[KPL], ex[KPL];
+#pragma unroll
+        for (int i = 0; i < KPL; ++i) {
+            const int k = lane + 32 * i;
+            x[i] = (k < K1) ? P.eta[(size_t)d * K1 + k] : 0.0;
+            mu[i] = (k < K1) ? P.mu[(size_t)d * K1 + k] : 0.0;
+            p[i] = 0.0; g[i] = 0.0; gt[i] = 0.0; xt[i] = 0.0; a[i] = 0.0; ex[i] = 0.0;
+        }
+        mbar_wait(mbar, parity);
+        parity ^= 1;
+        __syncwarp();
+
+        // ---- a_k = sum_v beta_kv c_v / colsum_v   (eta-independent part of df, stm.py:954) ----
+        for (int v = lane; v < n; v += 32) {
+            const float4* row = reinterpret_cast<const float4*>(tile + (size_t)v * TS);
+            double cs = 0.0;
+            for (int q = 0; q < TS / 4; ++q) {
+                const float4 b = row[q];
+                cs += (double)b.x; cs += (double)b.y; cs += (double)b.z; cs += (double)b.w;
+            }
+            wv[v] = (double)cw[v] / cs;
+        }
+        __syncwarp();
+        for (int v = 0; v < n; ++v) {
+            const double r = wv[v];
+#pragma unroll
+            for (int i = 0; i < KPL; ++i) {
+                const int k = lane + 32 * i;
+                if (k < K) a[i] += (double)tile[(size_t)v * TS + k] * r;
+            }
+        }
+        __syncwarp();
+
+        // =======================================================================================
+        // BFGS (scipy/optimize/_optimize.py:1345-1526) as a warp-uniform state machine with ONE
+        // objective-evaluation site.  Every evaluation returns f, the gradient gt and dphi = gt.p.
+        // =======================================================================================
+        int ls = LS_INIT, k_it = 0, warnflag = 0, nfev = 0, done = 0;
+        const int maxiter = K1 * 200;
+        double alpha = 0.0, f_eval = 0.0, dphi = 0.0;
+        double old_fval = 0.0, old_old_fval = 0.0, gnorm = 0.0, derphi0 = 0.0;
+        int have_cache = 0;
+        // dcsrch state
+        int brackt = 0, stage = 1, w1_it = 0;
+        double finit = 0, ginit = 0, gtest = 0, width = 0, width1 = 0;
+        double stx = 0, fx = 0, gx = 0, sty = 0, fy = 0, gy = 0, stmin = 0, stmax = 0;
+        // wolfe2 / zoom state
+        int w2_i = 0, z_i = 0;
+        double alpha0 = 0, phi_a0 = 0, derphi_a0 = 0;
+        double a_lo = 0, a_hi = 0, phi_lo = 0, phi_hi = 0, derphi_lo = 0, phi_rec = 0, a_rec = 0;
+
+        const double c1 = 1e-4, c2 = 0.9, xtol = 1e-14, stpmin = 1e-100, stpmax = 1e100;
+
+        while (!done) {
+            // ---------------- evaluate f, g at x + alpha p --------------------------------------
+            {
+                double xn[KPL];
+                bool same = have_cache;
+#pragma unroll
+                for (int i = 0; i < KPL; ++i) {
+                    xn[i] = __dadd_rn(x[i], __dmul_rn(alpha, p[i]));
+                    same = same && (xn[i] == xt[i]);
+                }
+                // ScalarFunction memoisation (scipy/_differentiable_functions.py:391-401):
+                // an identical trial point re-uses f and g
+                if (!__all_sync(STM_FULL, same)) {
+                    nfev++;
+                    have_cache = 1;
+                    double et[KPL];
+                    double m = -INFINITY;
+#pragma unroll
+                    for (int i = 0; i < KPL; ++i) {
+                        const int k = lane + 32 * i;
+                        xt[i] = xn[i];
+                        et[i] = (k < K1) ? xn[i] : ((k == K1) ? 0.0 : -INFINITY);
+                        m = nanmax(m, et[i]);
+                    }
+                    m = warp_max(m);
+                    double cnt_l = 0.0, s_l = 0.0, q_l = 0.0;
+#pragma unroll
+                    for (int i = 0; i < KPL; ++i) {
+                        const int k = lane + 32 * i;
+                        ex[i] = exp(et[i] - m);
+                        if (k < K) { if (et[i] == m) cnt_l += 1.0; else s_l += ex[i]; }
+                        v0[k] = (k < K) ? ex[i] : 0.0;
+                        const double dk = xt[i] - mu[i];
+                        q_l += (Sd[i] * dk) * dk;
+                    }
+                    __syncwarp();
+                    const double cnt = warp_sum(cnt_l);
+                    double ssum = warp_sum(s_l);
+                    const double se_all = ssum + cnt;
+                    if (ssum != 0.0) ssum = ssum / cnt;
+                    // scipy.special.logsumexp (scipy/special/_logsumexp.py:201-247)
+                    const double lse = log1p(ssum) + log(cnt) + m;
+                    const double quad = 0.5 * warp_sum(q_l);
+
+                    // data term: sum_v c_v (m + log(sum_k e_k beta_kv))           stm.py:938-941
+                    double part = 0.0;
+                    for (int w0 = 0; w0 < n; w0 += 32 * J) {
+                        double acc[J];
+                        const float4* rows[J];
+#pragma unroll
+                        for (int j = 0; j < J; ++j) {
+                            acc[j] = 0.0;
+                            int v = w0 + lane + 32 * j;
+                            if (v >= n) v = n - 1;
+                            rows[j] = reinterpret_cast<const float4*>(tile + (size_t)v * TS);
+                        }
+                        const double2* e2 = reinterpret_cast<const double2*>(v0);
+                        for (int q = 0; q < TS / 4; ++q) {
+                            const double2 ea = e2[2 * q], eb = e2[2 * q + 1];
+#pragma unroll
+                            for (int j = 0; j < J; ++j) {
+                                const float4 b = rows[j][q];
+                                acc[j] = fma(ea.x, (double)b.x, acc[j]);
+                                acc[j] = fma(ea.y, (double)b.y, acc[j]);
+                                acc[j] = fma(eb.x, (double)b.z, acc[j]);
+                                acc[j] = fma(eb.y, (double)b.w, acc[j]);
+                            }
+                        }
+#pragma unroll
+                        for (int j = 0; j < J; ++j) {
+                            const int v = w0 + lane + 32 * j;
+                            if (v < n) part += (double)cw[v] * (m + log(acc[j]));
+                        }
+                    }
+                    const double data = warp_sum(part);
+                    f_eval = quad - (data - Nint * lse);
+
+                    // gradient stm.py:946-958 (beta NOT weighted by exp(eta): reference quirk)
+                    const double scale = Nsum / se_all;
+#pragma unroll
+                    for (int i = 0; i < KPL; ++i) {
+                        const int k = lane + 32 * i;
+                        const double dk = xt[i] - mu[i];
+                        gt[i] = (k < K1) ? (Sd[i] * dk - (a[i] - scale * ex[i])) : 0.0;
+                    }
+                    __syncwarp();
+                }
+                double dp_l2 = 0.0;
+#pragma unroll
+                for (int i = 0; i < KPL; ++i) dp_l2 += gt[i] * p[i];
+                dphi = warp_sum(dp_l2);
+            }
+
+            // ---------------- consume the evaluation --------------------------------------------
+            int accept = 0;      // 1: step alpha accepted (f_eval, gt valid)
+            int fail = 0;        // 1: line search failed
+            int new_iter = 0;    // 1: start a new BFGS iteration (compute p, init wolfe1)
+            int start_w2 = 0;
+            int start_zoom = 0;
+            double zl = 0, zh = 0, zpl = 0, zph = 0, zdl = 0;
+
+            if (ls == LS_INIT) {
+                old_fval = f_eval;
+                double n2 = 0.0, gm = 0.0;
+#pragma unroll
+                for (int i = 0; i < KPL; ++i) {
+                    g[i] = gt[i];
+                    n2 += g[i] * g[i];
+                    gm = nanmax(gm, fabs(g[i]));
+                }
+                old_old_fval = old_fval + sqrt(warp_sum(n2)) / 2.0;
+                gnorm = warp_max(gm);
+                new_iter = 1;
+            } else if (ls == LS_W1) {
+                // one DCSRCH._iterate (scipy/optimize/_dcsrch.py:310-500) with (stp=alpha, f, g)
+                const double stp_in = alpha, f = f_eval, gd = dphi;
+                const double ftest = finit + stp_in * gtest;
+                int warn = 0;
+                if (stage == 1 && f <= ftest && gd >= 0.0) stage = 2;
+                if (brackt && (stp_in <= stmin || stp_in >= stmax)) warn = 1;
+                if (brackt && stmax - stmin <= xtol * stmax) warn = 1;
+                if (stp_in == stpmax && f <= ftest && gd <= gtest) warn = 1;
+                if (stp_in == stpmin && (f > ftest || gd >= gtest)) warn = 1;
+                if (f <= ftest && fabs(gd) <= c2 * -ginit) {
+                    accept = 1;
+                } else if (warn) {
+                    start_w2 = 1;
+                } else {
+                    double stp = stp_in;
+                    if (stage == 1 && f <= fx && f > ftest) {
+                        double fm = f - stp * gtest, fxm = fx - stx * gtest, fym = fy - sty * gtest;
+                        double gm = gd - gtest, gxm = gx - gtest, gym = gy - gtest;
+                        dcstep(stx, fxm, gxm, sty, fym, gym, stp, fm, gm, brackt, stmin, stmax);
+                        fx = fxm + stx * gtest; fy = fym + sty * gtest;
+                        gx = gxm + gtest; gy = gym + gtest;
+                    } else {
+                        dcstep(stx, fx, gx, sty, fy, gy, stp, f, gd, brackt, stmin, stmax);
+                    }
+                    if (brackt) {
+                        if (fabs(sty - stx) >= 0.66 * width1) stp = stx + 0.5 * (sty - stx);
+                        width1 = width;
+                        width = fabs(sty - stx);
+                        stmin = py_min2(stx, sty);
+                        stmax = py_max2(stx, sty);
+                    } else {
+                        stmin = stp + 1.1 * (stp - stx);
+                        stmax = stp + 4.0 * (stp - stx);
+                    }
+                    stp = np_clip(stp, stpmin, stpmax);
+                    if ((brackt && (stp <= stmin || stp >= stmax)) ||
+                        (brackt && stmax - stmin <= xtol * stmax))
+                        stp = stx;
+                    w1_it++;
+                    if (!isfinite(stp) || w1_it >= 100) start_w2 = 1;  // WARN / maxiter -> stp None
+                    else alpha = stp;
+                }
+            } else if (ls == LS_W2) {
+                // bracket phase of scalar_search_wolfe2 (scipy/optimize/_linesearch.py:411-466)
+                const double alpha1 = alpha, phi_a1 = f_eval, derphi_a1 = dphi;
+                if (w2_i == 10) {
+                    accept = 1;  // for-else: alpha_star = alpha1, derphi_star None (gradient re-evaluated)
+                } else if (alpha1 == 0.0 || alpha0 > 1e100) {
+                    fail = 1;
+                } else if (phi_a1 > old_fval + c1 * alpha1 * derphi0 || (phi_a1 >= phi_a0 && w2_i > 0)) {
+                    start_zoom = 1; zl = alpha0; zh = alpha1; zpl = phi_a0; zph = phi_a1; zdl = derphi_a0;
+                } else if (fabs(derphi_a1) <= -c2 * derphi0) {
+                    accept = 1;
+                } else if (derphi_a1 >= 0.0) {
+                    start_zoom = 1; zl = alpha1; zh = alpha0; zpl = phi_a1; zph = phi_a0; zdl = derphi_a1;
+                } else {
+                    const double alpha2 = py_min2(2.0 * alpha1, 1e100);
+                    alpha0 = alpha1; phi_a0 = phi_a1; derphi_a0 = derphi_a1;
+                    alpha = alpha2;
+                    w2_i++;
+                }
+            } else {  // LS_ZOOM — scipy/optimize/_linesearch.py:546-634
+                const double a_j = alpha, phi_aj = f_eval, derphi_aj = dphi;
+                if (phi_aj > old_fval + c1 * a_j * derphi0 || phi_aj >= phi_lo) {
+                    phi_rec = phi_hi; a_rec = a_hi; a_hi = a_j; phi_hi = phi_aj;
+                } else {
+                    if (fabs(derphi_aj) <= -c2 * derphi0) {
+                        accept = 1;
+                    } else {
+                        if (derphi_aj * (a_hi - a_lo) >= 0.0) {
+                            phi_rec = phi_hi; a_rec = a_hi; a_hi = a_lo; phi_hi = phi_lo;
+                        } else {
+                            phi_rec = phi_lo; a_rec = a_lo;
+                        }
+                        a_lo = a_j; phi_lo = phi_aj; derphi_lo = derphi_aj;
+                    }
+                }
+                if (!accept) {
+                    z_i++;
+                    if (z_i > 10) fail = 1;
+                }
+            }
+
+            if (start_w2) {
+                // scalar_search_wolfe2 prologue (scipy/optimize/_linesearch.py:395-409)
+                double alpha1;
+                if (derphi0 != 0.0) alpha1 = py_min2(1.0, 1.01 * 2 * (old_fval - old_old_fval) / derphi0);
+                else alpha1 = 1.0;
+                if (alpha1 < 0.0) alpha1 = 1.0;
+                alpha1 = py_min2(alpha1, 1e100);
+                alpha0 = 0.0; phi_a0 = old_fval; derphi_a0 = derphi0; w2_i = 0;
+                alpha = alpha1;
+                ls = LS_W2;
+            }
+            if (start_zoom) {
+                a_lo = zl; a_hi = zh; phi_lo = zpl; phi_hi = zph; derphi_lo = zdl;
+                phi_rec = old_fval; a_rec = 0.0; z_i = 0;
+                ls = LS_ZOOM;
+            }
+            if (ls == LS_ZOOM && !accept && !fail) {
+                // next trial step of _zoom
+                const double dalpha = a_hi - a_lo;
+                double za, zb;
+                if (dalpha < 0.0) { za = a_hi; zb = a_lo; } else { za = a_lo; zb = a_hi; }
+                double a_j = nan("");
+                double cchk = 0.0;
+                if (z_i > 0) {
+                    cchk = 0.2 * dalpha;
+                    a_j = cubicmin(a_lo, phi_lo, derphi_lo, a_hi, phi_hi, a_rec, phi_rec);
+                }
+                if (z_i == 0 || isnan(a_j) || a_j > zb - cchk || a_j < za + cchk) {
+                    const double qchk = 0.1 * dalpha;
+                    a_j = quadmin(a_lo, phi_lo, derphi_lo, a_hi, phi_hi);
+                    if (isnan(a_j) || a_j > zb - qchk || a_j < za + qchk) a_j = a_lo + 0.5 * dalpha;
+                }
+                alpha = a_j;
+            }
+
+            if (fail) { warnflag = 2; done = 1; }
+
+            if (accept) {
+                // _minimize_bfgs body after the line search (scipy/optimize/_optimize.py:1452-1498)
+                const double alpha_k = alpha;
+                double ys_l = 0.0, gm = 0.0, pm = 0.0;
+                double sk[KPL], yk[KPL];
+#pragma unroll
+                for (int i = 0; i < KPL; ++i) {
+                    sk[i] = __dmul_rn(alpha_k, p[i]);
+                    x[i] = xt[i];                 // xk + alpha_k*pk, same expression as the trial point
+                    yk[i] = gt[i] - g[i];
+                    g[i] = gt[i];
+                    ys_l += yk[i] * sk[i];
+                    gm = nanmax(gm, fabs(g[i]));
+                    pm = nanmax(pm, fabs(p[i]));
+                }
+                old_old_fval = old_fval;
+                old_fval = f_eval;
+                k_it++;
+                gnorm = warp_max(gm);
+                pm = warp_max(pm);
+                if (gnorm <= 1e-5) { done = 1; }
+                else if (alpha_k * pm <= 0.0) { done = 1; }
+                else if (!isfinite(old_fval)) { warnflag = 2; done = 1; }
+                else {
+                    const double rhok_inv = warp_sum(ys_l);
+                    const double rho = (rhok_inv == 0.0) ? 1000.0 : 1.0 / rhok_inv;
+                    // Hk <- (I - rho s y')(Hk)(I - rho y s') + rho s s'   as a symmetric rank-2 update:
+                    //   u = Hk y ;  Hk' = Hk - (rho u) s' - s (rho u)' + (rho^2 y'u + rho) s s'
+                    double u[KPL];
+                    if (k_it == 1) {
+#pragma unroll
+                        for (int i = 0; i < KPL; ++i) u[i] = yk[i];  // Hk = I
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < KPL; ++i) { u[i] = 0.0; v1[lane + 32 * i] = yk[i]; }
+                        __syncwarp();
+                        for (int r = 0; r < K1; ++r) {
+                            const double yr = v1[r];
+#pragma unroll
+                            for (int i = 0; i < KPL; ++i) {
+                                const int k = lane + 32 * i;
+                                if (k < K1) u[i] = fma(Hk[(size_t)r * K1 + k], yr, u[i]);
+                            }
+                        }
+                        __syncwarp();
+                    }
+                    double yu_l = 0.0;
+#pragma unroll
+                    for (int i = 0; i < KPL; ++i) yu_l += yk[i] * u[i];
+                    const double yu = warp_sum(yu_l);
+                    const double cc = rho * rho * yu + rho;
+                    double ru[KPL];
+#pragma unroll
+                    for (int i = 0; i < KPL; ++i) {
+                        const int k = lane + 32 * i;
+                        ru[i] = rho * u[i];
+                        v1[k] = sk[i]; v2[k] = ru[i]; v3[k] = g[i];
+                    }
+                    __syncwarp();
+                    // fused: write Hk' and accumulate p = -Hk' g
+                    double pn[KPL];
+#pragma unroll
+                    for (int i = 0; i < KPL; ++i) pn[i] = 0.0;
+                    for (int r = 0; r < K1; ++r) {
+                        const double sr = v1[r], rur = v2[r], gr = v3[r];
+#pragma unroll
+                        for (int i = 0; i < KPL; ++i) {
+                            const int k = lane + 32 * i;
+                            if (k < K1) {
+                                double h = (k_it == 1) ? ((r == k) ? 1.0 : 0.0) : Hk[(size_t)r * K1 + k];
+                                h = h - (__dmul_rn(rur, sk[i]) + __dmul_rn(sr, ru[i])) + cc * sr * sk[i];
+                                Hk[(size_t)r * K1 + k] = h;
+                                pn[i] = fma(h, gr, pn[i]);
+                            }
+                        }
+                    }
+                    __syncwarp();
+#pragma unroll
+                    for (int i = 0; i < KPL; ++i) p[i] = -pn[i];
+                    new_iter = 2;  // p already computed
+                }
+            }
+
+            if (new_iter && !done) {
+                if (!(gnorm > 1e-5) || !(k_it < maxiter)) {
+                    done = 1;
+                } else {
+                    if (new_iter == 1) {
+#pragma unroll
+                        for (int i = 0; i < KPL; ++i) p[i] = -g[i];  // Hk = I
+                    }
+                    double d_l = 0.0;
+#pragma unroll
+                    for (int i = 0; i < KPL; ++i) d_l += g[i] * p[i];
+                    derphi0 = warp_sum(d_l);
+                    // scalar_search_wolfe1 prologue + DCSRCH START
+                    double alpha1;
+                    if (derphi0 != 0.0) {
+                        alpha1 = py_min2(1.0, 1.01 * 2 * (old_fval - old_old_fval) / derphi0);
+                        if (alpha1 < 0.0) alpha1 = 1.0;
+                    } else alpha1 = 1.0;
+                    if (alpha1 < stpmin || alpha1 > stpmax || derphi0 >= 0.0 || !isfinite(alpha1)) {
+                        // task = ERROR -> stp None -> wolfe2
+                        double a1;
+                        if (derphi0 != 0.0) a1 = py_min2(1.0, 1.01 * 2 * (old_fval - old_old_fval) / derphi0);
+                        else a1 = 1.0;
+                        if (a1 < 0.0) a1 = 1.0;
+                        a1 = py_min2(a1, 1e100);
+                        alpha0 = 0.0; phi_a0 = old_fval; derphi_a0 = derphi0; w2_i = 0;
+                        alpha = a1;
+                        ls = LS_W2;
+                    } else {
+                        brackt = 0; stage = 1; finit = old_fval; ginit = derphi0; gtest = c1 * ginit;
+                        width = stpmax - stpmin; width1 = width / 0.5;
+                        stx = 0.0; fx = finit; gx = ginit; sty = 0.0; fy = finit; gy = ginit;
+                        stmin = 0.0; stmax = alpha1 + 4.0 * alpha1;
+                        w1_it = 1;  // the START call was iteration 0 of DCSRCH.__call__
+                        alpha = alpha1;
+                        ls = LS_W1;
+                    }
+                }
+            }
+        }  // BFGS loop
+
+        int status = warnflag;
+        if (status != 2) {
+            if (k_it >= maxiter) status = 1;
+            else {
+                bool bad = isnan(gnorm) || isnan(old_fval);
+#pragma unroll
+                for (int i = 0; i < KPL; ++i) bad = bad || isnan(x[i]);
+                status = __any_sync(STM_FULL, bad) ? 3 : 0;
+            }
+        }
+
+        // =======================================================================================
+        // post-optimisation: theta, phi -> beta_ss, Hessian, Cholesky, bound, nu -> sigma_ss
+        // =======================================================================================
+        double th[KPL], eu[KPL];  // stable softmax (stm.py:905-909), unshifted exp(eta~)
+        {
+            double et[KPL], m = -INFINITY, se_l = 0.0, ss_l = 0.0;
+#pragma unroll
+            for (int i = 0; i < KPL; ++i) {
+                const int k = lane + 32 * i;
+                et[i] = (k < K1) ? x[i] : ((k == K1) ? 0.0 : -INFINITY);
+                m = nanmax(m, et[i]);
+            }
+            m = warp_max(m);
+#pragma unroll
+            for (int i = 0; i < KPL; ++i) {
+                eu[i] = exp(et[i]);
+                th[i] = exp(et[i] - m);
+                se_l += eu[i];
+                ss_l += th[i];
+            }
+            const double se = warp_sum(se_l), ss = warp_sum(ss_l);
+#pragma unroll
+            for (int i = 0; i < KPL; ++i) {
+                const int k = lane + 32 * i;
+                th[i] = th[i] / ss;
+                if (k < K1) P.eta[(size_t)d * K1 + k] = x[i];
+                if (k < K) P.theta[(size_t)d * K + k] = eu[i] / se;  // stm.py:547-549 (no max shift)
+                v0[k] = (k < K) ? eu[i] : 0.0;
+                v1[k] = (k < K) ? th[i] * eu[i] : 0.0;
+            }
+            __syncwarp();
+        }
+        // colsum_v = sum_k e_k beta_kv and the log-likelihood part of the bound (stm.py:1088-1096)
+        double ll_l = 0.0;
+        for (int v = lane; v < n; v += 32) {
+            const float4* row = reinterpret_cast<const float4*>(tile + (size_t)v * TS);
+            const double2* e2 = reinterpret_cast<const double2*>(v0);
+            const double2* t2 = reinterpret_cast<const double2*>(v1);
+            double s = 0.0, t = 0.0;
+            for (int q = 0; q < TS / 4; ++q) {
+                const float4 b = row[q];
+                const double2 ea = e2[2 * q], eb = e2[2 * q + 1], ta = t2[2 * q], tb = t2[2 * q + 1];
+                s = fma(ea.x, (double)b.x, s); s = fma(ea.y, (double)b.y, s);
+                s = fma(eb.x, (double)b.z, s); s = fma(eb.y, (double)b.w, s);
+                t = fma(ta.x, (double)b.x, t); t = fma(ta.y, (double)b.y, t);
+                t = fma(tb.x, (double)b.z, t); t = fma(tb.y, (double)b.w, t);
+            }
+            const double c = (double)cw[v];
+            ll_l += log(t) * c;
+            wv[v] = sqrt(c) / s;   // sqrt(c_v)/colsum_v
+        }
+        const double loglik = warp_sum(ll_l);
+        __syncwarp();
+
+        // Hessian data term  sum_v b_v b_v'  with b_kv = beta_kv e_k sqrt(c_v)/colsum_v (stm.py:1000-1006),
+        // accumulated in BSxBS register blocks of the lower triangle; phi_kv = b_kv sqrt(c_v) is
+        // scattered into beta_ss on the way (stm.py:1103-1118, 582-590).
+        double rowsum[KPL];  // sum_v phi_kv  (np.sum(c, axis=1), stm.py:1011)
+#pragma unroll
+        for (int i = 0; i < KPL; ++i) rowsum[i] = 0.0;
+        {
+            constexpr int BS = (KPL == 1) ? 4 : 8;
+            const int nb = (K1 + BS - 1) / BS;
+            const int nblk = nb * (nb + 1) / 2;
+            double* beta_ss_a = P.beta_ss_t + (size_t)asp * P.V * TS;
+            for (int b0 = 0; b0 < nblk; b0 += 32) {
+                const int blk = b0 + lane;
+                // block index -> (br, bc) with bc <= br
+                int br = 0, bc = 0;
+                if (blk < nblk) {
+                    br = (int)((sqrt(8.0 * blk + 1.0) - 1.0) * 0.5);
+                    while ((br + 1) * (br + 2) / 2 <= blk) br++;
+                    while (br * (br + 1) / 2 > blk) br--;
+                    bc = blk - br * (br + 1) / 2;
+                }
+                double acc[BS][BS];
+#pragma unroll
+                for (int r = 0; r < BS; ++r)
+#pragma unroll
+                    for (int c = 0; c < BS; ++c) acc[r][c] = 0.0;
+                double* bbuf = v2;  // [2][KVS] double-buffered b vector (v2, v3 contiguous)
+                for (int v = 0; v < n; ++v) {
+                    double* bv = bbuf + (v & 1) * KVS;
+                    const double sc = wv[v];
+                    const double sqc = sqrt((double)cw[v]);
+#pragma unroll
+                    for (int i = 0; i < KPL; ++i) {
+                        const int k = lane + 32 * i;
+                        double bk = 0.0;
+                        if (k < K) {
+                            bk = ((double)tile[(size_t)v * TS + k] * eu[i]) * sc;
+                            if (b0 == 0) {
+                                const double ph = bk * sqc;
+                                rowsum[i] += ph;
+                                red_add_f64(beta_ss_a + (size_t)wid[v] * TS + k, ph);
+                            }
+                        }
+                        bv[k] = bk;
+                    }
+                    __syncwarp();
+                    if (blk < nblk) {
+                        double rv[BS], cv[BS];
+#pragma unroll
+                        for (int r = 0; r < BS; ++r) { rv[r] = bv[br * BS + r]; cv[r] = bv[bc * BS + r]; }
+#pragma unroll
+                        for (int r = 0; r < BS; ++r)
+#pragma unroll
+                            for (int c = 0; c < BS; ++c) acc[r][c] = fma(rv[r], cv[c], acc[r][c]);
+                    }
+                }
+                __syncwarp();
+                if (blk < nblk) {
+#pragma unroll
+                    for (int r = 0; r < BS; ++r)
+#pragma unroll
+                        for (int c = 0; c < BS; ++c) {
+                            const int gi = br * BS + r, gj = bc * BS + c;
+                            if (gi < K1 && gj < K1 && gj <= gi) Hg[(size_t)gi * K1 + gj] = acc[r][c];
+                        }
+                }
+            }
+        }
+        __syncwarp();
+        __threadfence_block();
+        // assemble H = data - N theta theta' + diag(-rowsum + N theta) + siginv into smem (tile is dead)
+#pragma unroll
+        for (int i = 0; i < KPL; ++i) {
+            const int k = lane + 32 * i;
+            v0[k] = th[i]; v1[k] = rowsum[i];
+        }
+        __syncwarp();
+        for (int r = 0; r < K1; ++r) {
+            const double thr = v0[r];
+#pragma unroll
+            for (int i = 0; i < KPL; ++i) {
+                const int k = lane + 32 * i;
+                if (k <= r) {
+                    double h = __ldcg(&Hg[(size_t)r * K1 + k]) - Nsum * (thr * th[i]);
+                    if (k == r) h = (h - rowsum[i] + Nsum * th[i]) + Sd[i];
+                    Hm[(size_t)r * HS + k] = h;
+                    Hm[(size_t)k * HS + r] = h;
+                }
+            }
+        }
+        __syncwarp();
+
+        // PD test + repairs (stm.py:1017-1021, 1039-1048).  "all eigenvalues > 0" is restated as
+        // "Cholesky succeeds".  The factor overwrites the strict lower triangle + a separate diagonal
+        // so the matrix can be restored from its upper triangle for the retries.
+        int repair = 0;
+        double* Ld = v2;      // diagonal of L
+        double* Dg = v3;      // diagonal of H (original / repaired)
+        for (int k = lane; k < K1; k += 32) Dg[k] = Hm[(size_t)k * HS + k];
+        __syncwarp();
+        int upper = 0;
+        for (int attempt = 0;; ++attempt) {
+            // left-looking Cholesky: lane owns rows
+            int ok = 1;
+            for (int j = 0; j < K1 && ok; ++j) {
+                // d = H_jj - sum_k<j L_jk^2
+                double s_l = 0.0;
+                for (int k = lane; k < j; k += 32) { const double l = Hm[(size_t)j * HS + k]; s_l = fma(l, l, s_l); }
+                const double djj = Dg[j] - warp_sum(s_l);
+                if (!(djj > 0.0)) { ok = 0; break; }
+                const double ljj = sqrt(djj);
+                if (lane == 0) Ld[j] = ljj;
+                for (int i = j + 1 + lane; i < K1; i += 32) {
+                    double t = Hm[(size_t)j * HS + i];  // upper triangle holds the original H_ij
+                    for (int k = 0; k < j; ++k) t = fma(-Hm[(size_t)i * HS + k], Hm[(size_t)j * HS + k], t);
+                    Hm[(size_t)i * HS + j] = t / ljj;
+                }
+                __syncwarp();
+            }
+            if (ok) break;
+            // failed: restore the lower triangle from the upper one, then repair
+            __syncwarp();
+            for (int r = 0; r < K1; ++r)
+                for (int k = lane; k < r; k += 32) Hm[(size_t)r * HS + k] = Hm[(size_t)k * HS + r];
+            __syncwarp();
+            if (attempt == 0 || attempt == 2 || attempt == 3) {
+                // make_pd (stm.py:964-984): d_i <- max(d_i, sum_j!=i |H_ij|)
+                for (int i = lane; i < K1; i += 32) {
+                    double tot = 0.0;
+                    for (int k = 0; k < K1; ++k) if (k != i) tot += fabs(Hm[(size_t)i * HS + k]);
+                    tot += fabs(Dg[i]);
+                    const double mag = tot - fabs(Dg[i]);
+                    if (Dg[i] < mag) Dg[i] = mag;
+                }
+            }
+            if (attempt == 1 || attempt == 3) {
+                for (int i = lane; i < K1; i += 32) Dg[i] += 1e-5;
+            }
+            if (attempt == 0) repair = 1;            // hessian(): make_pd
+            else if (attempt == 1) repair = 2;       // hessian(): + 1e-5
+            else if (attempt == 2) repair += 4;      // decompose_hessian(): make_pd
+            else if (attempt == 3) { repair += 8; upper = 1; }  // scipy.linalg.cholesky (upper) of make_pd + 1e-5 I
+            else {
+                for (int k = lane; k < K1; k += 32) Ld[k] = nan("");
+                __syncwarp();
+                break;
+            }
+            __syncwarp();
+        }
+        __syncwarp();
+
+        // bound (stm.py:1085-1100)
+        double det_l = 0.0, q_l = 0.0;
+        for (int k = lane; k < K1; k += 32) det_l += log(Ld[k]);
+#pragma unroll
+        for (int i = 0; i < KPL; ++i) { const double dk = x[i] - mu[i]; q_l += (Sd[i] * dk) * dk; }
+        const double bound = loglik - warp_sum(det_l) - 0.5 * warp_sum(q_l) - sigmaentropy;
+        if (lane == 0) {
+            P.doc_bound[d] = bound;
+            const int nit_c = k_it > 0xfffff ? 0xfffff : k_it;
+            P.doc_info[d] = status | (nit_c << 4) | (repair << 24);
+            P.doc_nfev[d] = nfev;
+        }
+
+        // nu = H^-1 = L^-T L^-1 (stm.py:1052-1066), accumulated into sigma_ss (stm.py:582)
+        if (!upper) {
+            // Li = L^-1 (lower), stored transposed in the UPPER triangle: Hm[j][i] = Li[i][j], i >= j.
+            // Row i of Li for all columns j < i in parallel (lane <-> j):
+            //   Li[i][j] = -(sum_{k=j}^{i-1} L[i][k] Li[k][j]) / L[i][i],   Li[i][i] = 1 / L[i][i]
+            for (int i = 0; i < K1; ++i) {
+                const double inv = 1.0 / Ld[i];
+                for (int j = lane; j < i; j += 32) {
+                    double t = 0.0;
+                    for (int k = j; k < i; ++k) t = fma(Hm[(size_t)i * HS + k], Hm[(size_t)j * HS + k], t);
+                    Hm[(size_t)j * HS + i] = -t * inv;
+                }
+                if (lane == 0) Hm[(size_t)i * HS + i] = inv;
+                __syncwarp();
+            }
+            // nu_ij = sum_{k>=i} Li[k][i] Li[k][j]  (i >= j): row i of the upper storage dotted with row j
+            for (int idx = lane; idx < K1 * (K1 + 1) / 2; idx += 32) {
+                int i = (int)((sqrt(8.0 * idx + 1.0) - 1.0) * 0.5);
+                while ((i + 1) * (i + 2) / 2 <= idx) i++;
+                while (i * (i + 1) / 2 > idx) i--;
+                const int j = idx - i * (i + 1) / 2;
+                double t = 0.0;
+                for (int k = i; k < K1; ++k) t = fma(Hm[(size_t)i * HS + k], Hm[(size_t)j * HS + k], t);
+                red_add_f64(sig_acc + (size_t)i * K1 + j, t);
+            }
+        } else {
+            for (int k = lane; k < K1; k += 32) {
+                const double il = 1.0 / Ld[k];
+                red_add_f64(sig_acc + (size_t)k * K1 + k, il * il);
+            }
+        }
+        __syncwarp();
+    }  // document loop
+}
+
+}  // namespace stm

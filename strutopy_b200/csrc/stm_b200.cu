@@ -1,0 +1,801 @@
+// stm_b200.cu — host side of libstm_b200.so: context, corpus residency, launch configuration,
+// M-step (cuBLAS moments + cuSOLVER factorisations + small fp64 kernels), and the C ABI declared in
+// include/stm_b200.h.  Reference behaviour cited per function (stm.py = /root/reference/src/modules/stm.py).
+#include "../../include/stm_b200.h"
+#include "estep_kernel.cuh"
+
+#include <cublas_v2.h>
+#include <cusolverDn.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+namespace {
+
+thread_local std::string g_create_error;
+
+struct LengthClass {
+    int n_cap = 0;       // tile rows per warp
+    int J = 0;           // words per lane per pass (template parameter)
+    int n_docs = 0;
+    int* d_docs = nullptr;
+    int warps = 0;       // warps per CTA
+    int smem_per_warp = 0;
+    int grid = 0;
+};
+
+}  // namespace
+
+struct stm_ctx {
+    int device = 0, K = 0, K1 = 0, V = 0, A = 1, TS = 0, KPL = 0;
+    int sm_count = 0, max_smem = 0;
+    int64_t D = 0, nnz = 0;
+    int n_max = 0;
+    long long* d_doc_ptr = nullptr;
+    int* d_word_id = nullptr;
+    float* d_count = nullptr;
+    int* d_aspect = nullptr;
+    std::vector<LengthClass> classes;
+    unsigned int* d_queues = nullptr;
+    double* d_scratch = nullptr;
+    long long scratch_stride = 0;
+    int max_warps_total = 0;
+    double* d_sigma_rep = nullptr;
+    int n_rep = 0;
+    // M-step workspaces
+    double* d_ones = nullptr;      // [D]
+    double* d_msmall = nullptr;    // small fp64 workspace
+    int64_t msmall_len = 0;
+    double* d_colsum_part = nullptr;
+    int colsum_blocks = 0;
+    double* d_potrf_work = nullptr;
+    int potrf_lwork = 0;
+    double* d_syevd_work = nullptr;
+    int syevd_lwork = 0;
+    int syevd_p = -1;
+    int* d_info = nullptr;
+    // host-API device buffers
+    double *h_beta_kv = nullptr, *h_mu = nullptr, *h_eta = nullptr, *h_theta = nullptr, *h_stats = nullptr,
+           *h_prior = nullptr, *h_doc_bound = nullptr, *h_bss_kv = nullptr;
+    float* h_beta_t = nullptr;
+    int32_t *h_doc_info = nullptr, *h_doc_nfev = nullptr;
+    bool host_bufs = false;
+    cublasHandle_t cublas = nullptr;
+    cusolverDnHandle_t cusolver = nullptr;
+    int64_t launches = 0;
+    std::string err;
+};
+
+namespace {
+
+int fail(stm_ctx* c, int code, const std::string& msg) {
+    if (c) c->err = msg; else g_create_error = msg;
+    return code;
+}
+#define CU(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess)                                                                     \
+            return fail(ctx, STM_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_));    \
+    } while (0)
+#define CB(call)                                                                                   \
+    do {                                                                                           \
+        cublasStatus_t s_ = (call);                                                                \
+        if (s_ != CUBLAS_STATUS_SUCCESS)                                                           \
+            return fail(ctx, STM_ERR_CUDA, std::string(#call) + ": cublas status " + std::to_string((int)s_)); \
+    } while (0)
+#define CS(call)                                                                                   \
+    do {                                                                                           \
+        cusolverStatus_t s_ = (call);                                                              \
+        if (s_ != CUSOLVER_STATUS_SUCCESS)                                                         \
+            return fail(ctx, STM_ERR_CUDA, std::string(#call) + ": cusolver status " + std::to_string((int)s_)); \
+    } while (0)
+
+int beta_stride(int K) {
+    int ts = (K + 3) / 4 * 4;
+    if (((ts / 4) & 1) == 0) ts += 4;
+    return ts;
+}
+
+size_t smem_per_warp_bytes(int n_cap, int TS, int K1, int KPL) {
+    const int HS = K1 | 1;
+    size_t tile = (size_t)n_cap * TS * 4;
+    const size_t hb = (size_t)K1 * HS * 8;
+    if (hb > tile) tile = hb;
+    tile = (tile + 127) & ~(size_t)127;
+    const int KVS = KPL * 32 + 8;
+    size_t total = tile + (size_t)n_cap * 8 + (size_t)4 * KVS * 8 + (size_t)n_cap * 4 + (size_t)n_cap * 4 + 8;
+    return (total + 127) & ~(size_t)127;
+}
+
+}  // namespace
+// one translation unit per KPL (estep_inst.cu compiled with -DSTM_KPL=n) so the 16 kernel
+// instantiations build in parallel
+cudaError_t stm_launch_kpl1(const stm::EstepParams&, int, int, int, size_t, cudaStream_t);
+cudaError_t stm_launch_kpl2(const stm::EstepParams&, int, int, int, size_t, cudaStream_t);
+cudaError_t stm_launch_kpl3(const stm::EstepParams&, int, int, int, size_t, cudaStream_t);
+cudaError_t stm_launch_kpl4(const stm::EstepParams&, int, int, int, size_t, cudaStream_t);
+namespace {
+
+cudaError_t launch_class(int KPL, const stm::EstepParams& P, int J, int grid, int block, size_t smem,
+                         cudaStream_t st) {
+    switch (KPL) {
+        case 1: return stm_launch_kpl1(P, J, grid, block, smem, st);
+        case 2: return stm_launch_kpl2(P, J, grid, block, smem, st);
+        case 3: return stm_launch_kpl3(P, J, grid, block, smem, st);
+        default: return stm_launch_kpl4(P, J, grid, block, smem, st);
+    }
+}
+
+// ---- small device kernels ----------------------------------------------------------------------
+
+// E-step epilogue: sigma_ss = mirror(sum of replicas), bound = ordered sum of doc_bound, n_docs.
+__global__ void estep_epilogue_kernel(const double* __restrict__ sig_rep, int n_rep, int K1,
+                                      const double* __restrict__ doc_bound, long long D,
+                                      double* __restrict__ sigma_ss, double* __restrict__ bound,
+                                      double* __restrict__ ndocs) {
+    __shared__ double red[1024];
+    const int t = threadIdx.x;
+    for (int idx = t; idx < K1 * K1; idx += blockDim.x) {
+        const int i = idx / K1, j = idx % K1;
+        const int lo = (i >= j) ? (i * K1 + j) : (j * K1 + i);
+        double s = 0.0;
+        for (int r = 0; r < n_rep; ++r) s += sig_rep[(size_t)r * K1 * K1 + lo];
+        sigma_ss[idx] = s;
+    }
+    // fixed-order (deterministic) sum of the per-document bounds
+    double s = 0.0;
+    for (long long d = t; d < D; d += blockDim.x) s += doc_bound[d];
+    red[t] = s;
+    __syncthreads();
+    for (int o = blockDim.x / 2; o > 0; o >>= 1) {
+        if (t < o) red[t] += red[t + o];
+        __syncthreads();
+    }
+    if (t == 0) { *bound = red[0]; *ndocs = (double)D; }
+}
+
+// prior = { 1 / L_ii^2, sum log L_ii } from the potrf factor (column-major lower == row-major upper)
+__global__ void prior_from_chol_kernel(const double* __restrict__ L, int K1, const int* __restrict__ info,
+                                       double* __restrict__ prior) {
+    if (threadIdx.x == 0) {
+        double ent = 0.0;
+        const bool bad = (*info != 0);
+        for (int i = 0; i < K1; ++i) {
+            const double l = L[(size_t)i * K1 + i];
+            ent += log(l);
+            const double il = 1.0 / l;
+            prior[i] = bad ? nan("") : il * il;
+        }
+        prior[K1] = bad ? nan("") : ent;
+    }
+}
+
+__global__ void beta_to_wordmajor_kernel(const double* __restrict__ src, float* __restrict__ dst, int A,
+                                         int K, int V, int TS) {
+    const long long total = (long long)A * V * TS;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        const int k = (int)(i % TS);
+        const long long av = i / TS;
+        const int v = (int)(av % V);
+        const int a = (int)(av / V);
+        dst[i] = (k < K) ? (float)src[((size_t)a * K + k) * V + v] : 0.0f;
+    }
+}
+__global__ void wordmajor_to_kv_kernel(const double* __restrict__ src, double* __restrict__ dst, int A,
+                                       int K, int V, int TS) {
+    const long long total = (long long)A * K * V;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        const int v = (int)(i % V);
+        const long long ak = i / V;
+        const int k = (int)(ak % K);
+        const int a = (int)(ak / K);
+        dst[i] = src[((size_t)a * V + v) * TS + k];
+    }
+}
+
+// update_beta, A == 1: column sums over the vocabulary, two-stage and order-deterministic
+__global__ void colsum_partial_kernel(const double* __restrict__ ss, int V, int TS, int rows_per_block,
+                                      double* __restrict__ part) {
+    const int k = threadIdx.x;
+    if (k >= TS) return;
+    const int v0 = blockIdx.x * rows_per_block;
+    const int v1 = min(V, v0 + rows_per_block);
+    double s = 0.0;
+    for (int v = v0; v < v1; ++v) s += ss[(size_t)v * TS + k];
+    part[(size_t)blockIdx.x * TS + k] = s;
+}
+__global__ void colsum_final_kernel(const double* __restrict__ part, int nblk, int TS, double* __restrict__ out) {
+    const int k = threadIdx.x;
+    if (k >= TS) return;
+    double s = 0.0;
+    for (int b = 0; b < nblk; ++b) s += part[(size_t)b * TS + k];
+    out[k] = s;
+}
+// beta = beta_ss / rowsum (zero-safe), stm.py:741-745
+__global__ void beta_normalise_kernel(const double* __restrict__ ss, const double* __restrict__ rowsum, int V,
+                                      int K, int TS, float* __restrict__ beta_t, double* __restrict__ beta64_t) {
+    const long long total = (long long)V * TS;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        const int k = (int)(i % TS);
+        double b = 0.0;
+        if (k < K) {
+            const double rs = rowsum[k];
+            if (rs != 0.0) b = ss[i] / rs;
+        }
+        beta_t[i] = (float)b;
+        if (beta64_t) beta64_t[i] = b;
+    }
+}
+// A > 1: the reference's np.sum(beta_ss, axis=1) on an A x K x V array sums over TOPICS (stm.py:741)
+__global__ void beta_normalise_aspect_kernel(const double* __restrict__ ss, long long AV, int K, int TS,
+                                             float* __restrict__ beta_t, double* __restrict__ beta64_t) {
+    for (long long r = blockIdx.x * (long long)blockDim.x + threadIdx.x; r < AV;
+         r += (long long)gridDim.x * blockDim.x) {
+        const double* row = ss + (size_t)r * TS;
+        double s = 0.0;
+        for (int k = 0; k < K; ++k) s += row[k];
+        for (int k = 0; k < TS; ++k) {
+            double b = 0.0;
+            if (k < K && s != 0.0) b = row[k] / s;
+            beta_t[(size_t)r * TS + k] = (float)b;
+            if (beta64_t) beta64_t[(size_t)r * TS + k] = b;
+        }
+    }
+}
+
+// update_mu (OLS) + update_sigma on the reduced moments: one block, fp64.
+// Workspace layout `w` (doubles): G[p*p] (in: centred Gram, out of syevd: eigenvectors, column-major),
+// lam[p], R[p*K1] centred X'eta, gamma_t [p*K1] (out).
+__global__ void center_moments_kernel(const double* __restrict__ stats, const long long* __restrict__ off,
+                                      int p, int K1, double* __restrict__ G, double* __restrict__ R) {
+    const double N = stats[off[3]];
+    const double* sum_eta = stats + off[4];
+    const double* sum_x = stats + off[5];
+    const double* xtx = stats + off[6];
+    const double* xte = stats + off[7];
+    for (int idx = threadIdx.x; idx < p * p; idx += blockDim.x) {
+        const int i = idx / p, j = idx % p;
+        G[idx] = xtx[idx] - (sum_x[i] / N) * sum_x[j];
+    }
+    for (int idx = threadIdx.x; idx < p * K1; idx += blockDim.x) {
+        const int i = idx / K1, k = idx % K1;
+        R[idx] = xte[idx] - (sum_x[i] / N) * sum_eta[k];
+    }
+}
+// gamma_t [p][K1] = pinv(G) R with scipy.linalg.lstsq(cond=1e-6) semantics on the centred design:
+// singular values of Xc are sqrt(lam); those <= 1e-6 * max are dropped (min-norm solution).
+__global__ void solve_gamma_kernel(const double* __restrict__ Vec /*col-major p x p*/, const double* __restrict__ lam,
+                                   const double* __restrict__ R, int p, int K1, double* __restrict__ tmp /*p*K1*/,
+                                   double* __restrict__ gamma_t) {
+    double lmax = 0.0;
+    for (int i = 0; i < p; ++i) lmax = fmax(lmax, lam[i]);
+    const double cut = 1e-12 * lmax;  // (1e-6)^2 on eigenvalues of Xc'Xc
+    // tmp[e][k] = (V[:,e] . R[:,k]) / lam_e
+    for (int idx = threadIdx.x; idx < p * K1; idx += blockDim.x) {
+        const int e = idx / K1, k = idx % K1;
+        double s = 0.0;
+        for (int i = 0; i < p; ++i) s += Vec[(size_t)e * p + i] * R[(size_t)i * K1 + k];
+        tmp[idx] = (lam[e] > cut && lam[e] > 0.0) ? s / lam[e] : 0.0;
+    }
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < p * K1; idx += blockDim.x) {
+        const int i = idx / K1, k = idx % K1;
+        double s = 0.0;
+        for (int e = 0; e < p; ++e) s += Vec[(size_t)e * p + i] * tmp[(size_t)e * K1 + k];
+        gamma_t[idx] = s;
+    }
+}
+// sigma = ((eta-mu)'(eta-mu) + sigma_ss)/N with the residual Gram expanded from the global moments,
+// then the sigprior shrinkage (stm.py:723-728).  mode: 0 STM (mu = X gamma'), 1 CTM (mu = mean eta).
+__global__ void sigma_update_kernel(const double* __restrict__ stats, const long long* __restrict__ off, int p,
+                                    int K1, int model, const double* __restrict__ gamma_t, double sigprior,
+                                    double* __restrict__ tmp /* p*K1 */, double* __restrict__ sigma) {
+    const double N = stats[off[3]];
+    const double* sigma_ss = stats + off[1];
+    const double* sum_eta = stats + off[4];
+    const double* xtx = stats + off[6];
+    const double* xte = stats + off[7];
+    const double* ete = stats + off[8];
+    if (model == STM_MODEL_STM) {
+        // tmp[i][k] = sum_j xtx[i][j] gamma_t[j][k]
+        for (int idx = threadIdx.x; idx < p * K1; idx += blockDim.x) {
+            const int i = idx / K1, k = idx % K1;
+            double s = 0.0;
+            for (int j = 0; j < p; ++j) s += xtx[(size_t)i * p + j] * gamma_t[(size_t)j * K1 + k];
+            tmp[idx] = s;
+        }
+        __syncthreads();
+    }
+    for (int idx = threadIdx.x; idx < K1 * K1; idx += blockDim.x) {
+        const int a = idx / K1, b = idx % K1;
+        double cov;
+        if (model == STM_MODEL_STM) {
+            // (eta - X g')'(eta - X g') = ete - T' - T + g (xtx) g',  T[a][b] = sum_i gamma_t[i][a] xte[i][b]
+            double t_ab = 0.0, t_ba = 0.0, q = 0.0;
+            for (int i = 0; i < p; ++i) {
+                t_ab += gamma_t[(size_t)i * K1 + a] * xte[(size_t)i * K1 + b];
+                t_ba += gamma_t[(size_t)i * K1 + b] * xte[(size_t)i * K1 + a];
+                q += gamma_t[(size_t)i * K1 + a] * tmp[(size_t)i * K1 + b];
+            }
+            cov = ete[idx] - t_ab - t_ba + q;
+        } else {
+            cov = ete[idx] - (sum_eta[a] / N) * sum_eta[b];
+        }
+        const double s = (cov + sigma_ss[idx]) / N;
+        sigma[idx] = (a == b) ? (s * sigprior + (1.0 - sigprior) * s) : ((1.0 - sigprior) * s);
+    }
+}
+__global__ void mu_ctm_kernel(const double* __restrict__ stats, const long long* __restrict__ off, int K1,
+                              long long D, double* __restrict__ mu) {
+    const double N = stats[off[3]];
+    const double* sum_eta = stats + off[4];
+    const long long total = D * K1;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x)
+        mu[i] = sum_eta[i % K1] / N;
+}
+__global__ void fill_kernel(double* p, long long n, double v) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+        p[i] = v;
+}
+__global__ void unpack_info_kernel(const int* __restrict__ info, long long D, int* status, int* nit, int* repair) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < D; i += (long long)gridDim.x * blockDim.x) {
+        const int w = info[i];
+        if (status) status[i] = w & 0xf;
+        if (nit) nit[i] = (w >> 4) & 0xfffff;
+        if (repair) repair[i] = (w >> 24) & 0xff;
+    }
+}
+
+void layout(const stm_ctx* c, int p, int64_t* off) {
+    const int64_t K1 = c->K1;
+    int64_t o = 0;
+    off[0] = o; o += (int64_t)c->A * c->V * c->TS;
+    off[1] = o; o += K1 * K1;
+    off[2] = o; o += 1;
+    off[3] = o; o += 1;
+    off[4] = o; o += K1;
+    off[5] = o; o += p;
+    off[6] = o; o += (int64_t)p * p;
+    off[7] = o; o += (int64_t)p * K1;
+    off[8] = o; o += K1 * K1;
+    off[9] = o;
+}
+
+void free_corpus(stm_ctx* c) {
+    cudaFree(c->d_doc_ptr); cudaFree(c->d_word_id); cudaFree(c->d_count); cudaFree(c->d_aspect);
+    c->d_doc_ptr = nullptr; c->d_word_id = nullptr; c->d_count = nullptr; c->d_aspect = nullptr;
+    for (auto& lc : c->classes) cudaFree(lc.d_docs);
+    c->classes.clear();
+    cudaFree(c->d_queues); c->d_queues = nullptr;
+    cudaFree(c->d_scratch); c->d_scratch = nullptr;
+    cudaFree(c->d_sigma_rep); c->d_sigma_rep = nullptr;
+    cudaFree(c->d_ones); c->d_ones = nullptr;
+    cudaFree(c->d_colsum_part); c->d_colsum_part = nullptr;
+    if (c->host_bufs) {
+        cudaFree(c->h_beta_kv); cudaFree(c->h_mu); cudaFree(c->h_eta); cudaFree(c->h_theta);
+        cudaFree(c->h_stats); cudaFree(c->h_prior); cudaFree(c->h_doc_bound); cudaFree(c->h_bss_kv);
+        cudaFree(c->h_beta_t); cudaFree(c->h_doc_info); cudaFree(c->h_doc_nfev);
+        c->host_bufs = false;
+    }
+}
+
+}  // namespace
+
+// =================================================================================================
+// C ABI
+// =================================================================================================
+extern "C" {
+
+int stm_beta_stride(int K) { return beta_stride(K); }
+
+const char* stm_last_error(const stm_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+
+int64_t stm_launch_count(const stm_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+int stm_create(int device, int K, int V, int A, stm_ctx** out) {
+    stm_ctx* ctx = nullptr;
+    if (!out) return fail(ctx, STM_ERR_INVALID, "out is NULL");
+    *out = nullptr;
+    if (K < 2) return fail(ctx, STM_ERR_INVALID, "Number of topics must be >= 2");  // stm.py:393-394
+    if (K > 128) return fail(ctx, STM_ERR_UNSUPPORTED, "K > 128 is not supported by the warp-per-document kernel");
+    if (V < 1 || A < 1) return fail(ctx, STM_ERR_INVALID, "V and A must be >= 1");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+        return fail(ctx, STM_ERR_CUDA, "no CUDA device available (this library has no CPU fallback)");
+    if (device < 0 || device >= ndev) return fail(ctx, STM_ERR_INVALID, "bad device index");
+    cudaError_t e = cudaSetDevice(device);
+    if (e != cudaSuccess) return fail(ctx, STM_ERR_CUDA, cudaGetErrorString(e));
+    cudaDeviceProp prop;
+    e = cudaGetDeviceProperties(&prop, device);
+    if (e != cudaSuccess) return fail(ctx, STM_ERR_CUDA, cudaGetErrorString(e));
+    if (prop.major < 10)
+        return fail(ctx, STM_ERR_UNSUPPORTED, "libstm_b200 is built for sm_100a (Blackwell B200) only");
+    stm_ctx* c = new stm_ctx();
+    c->device = device; c->K = K; c->K1 = K - 1; c->V = V; c->A = A;
+    c->TS = beta_stride(K);
+    c->KPL = (K + 31) / 32;
+    c->sm_count = prop.multiProcessorCount;
+    c->max_smem = (int)prop.sharedMemPerBlockOptin;
+    if (cublasCreate(&c->cublas) != CUBLAS_STATUS_SUCCESS || cusolverDnCreate(&c->cusolver) != CUSOLVER_STATUS_SUCCESS) {
+        delete c;
+        return fail(ctx, STM_ERR_CUDA, "cuBLAS / cuSOLVER handle creation failed");
+    }
+    cublasSetPointerMode(c->cublas, CUBLAS_POINTER_MODE_HOST);
+    // small M-step workspace
+    c->msmall_len = 4096 + 8LL * c->K1 * c->K1;
+    if (cudaMalloc(&c->d_msmall, sizeof(double) * c->msmall_len) != cudaSuccess ||
+        cudaMalloc(&c->d_info, sizeof(int) * 4) != cudaSuccess) {
+        delete c;
+        return fail(ctx, STM_ERR_CUDA, "workspace allocation failed");
+    }
+    cusolverDnDpotrf_bufferSize(c->cusolver, CUBLAS_FILL_MODE_LOWER, c->K1, c->d_msmall, c->K1, &c->potrf_lwork);
+    if (c->potrf_lwork < 1) c->potrf_lwork = 1;
+    cudaMalloc(&c->d_potrf_work, sizeof(double) * c->potrf_lwork);
+    *out = c;
+    return STM_OK;
+}
+
+void stm_destroy(stm_ctx* c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    free_corpus(c);
+    cudaFree(c->d_msmall); cudaFree(c->d_info); cudaFree(c->d_potrf_work); cudaFree(c->d_syevd_work);
+    if (c->cublas) cublasDestroy(c->cublas);
+    if (c->cusolver) cusolverDnDestroy(c->cusolver);
+    delete c;
+}
+
+int stm_set_corpus(stm_ctx* ctx, int64_t D, const int64_t* doc_ptr, const int32_t* word_id, const float* count,
+                   const int32_t* aspect) {
+    if (!ctx) return STM_ERR_INVALID;
+    if (D < 0 || !doc_ptr) return fail(ctx, STM_ERR_INVALID, "documents must be specified to establish input space");
+    CU(cudaSetDevice(ctx->device));
+    if (doc_ptr[0] != 0) return fail(ctx, STM_ERR_INVALID, "doc_ptr[0] must be 0");
+    const int64_t nnz = doc_ptr[D];
+    int n_max = 0;
+    for (int64_t d = 0; d < D; ++d) {
+        const int64_t n = doc_ptr[d + 1] - doc_ptr[d];
+        if (n < 0 || n > (1 << 24)) return fail(ctx, STM_ERR_INVALID, "doc_ptr must be non-decreasing");
+        n_max = std::max<int>(n_max, (int)n);
+    }
+    for (int64_t i = 0; i < nnz; ++i)
+        if (word_id[i] < 0 || word_id[i] >= ctx->V) return fail(ctx, STM_ERR_INVALID, "word id out of range [0, V)");
+    if (aspect) {
+        for (int64_t d = 0; d < D; ++d)
+            if (aspect[d] < 0 || aspect[d] >= ctx->A) return fail(ctx, STM_ERR_INVALID, "aspect out of range [0, A)");
+    }
+    free_corpus(ctx);
+    ctx->D = D; ctx->nnz = nnz; ctx->n_max = n_max;
+
+    // ---- length classes: tile capacity per warp -> warps per CTA -------------------------------
+    const int caps[] = {64, 128, 160, 256, 384, 512, 768, 1024, 1536, 2048, 3072, 4096, 6144, 8192};
+    const int ncaps = (int)(sizeof(caps) / sizeof(caps[0]));
+    std::vector<std::vector<int>> members(ncaps);
+    for (int64_t d = 0; d < D; ++d) {
+        const int n = (int)(doc_ptr[d + 1] - doc_ptr[d]);
+        int ci = 0;
+        while (ci < ncaps && caps[ci] < n) ci++;
+        if (ci == ncaps)
+            return fail(ctx, STM_ERR_UNSUPPORTED, "document with more than 8192 distinct words");
+        members[ci].push_back((int)d);
+    }
+    int max_warps = 0;
+    for (int ci = 0; ci < ncaps; ++ci) {
+        if (members[ci].empty()) continue;
+        LengthClass lc;
+        lc.n_cap = caps[ci];
+        lc.J = lc.n_cap <= 64 ? 2 : (lc.n_cap <= 128 ? 4 : (lc.n_cap <= 160 ? 5 : 8));
+        lc.n_docs = (int)members[ci].size();
+        // longest documents first: better tail balance on the dynamic queue
+        std::stable_sort(members[ci].begin(), members[ci].end(), [&](int a, int b) {
+            return (doc_ptr[a + 1] - doc_ptr[a]) > (doc_ptr[b + 1] - doc_ptr[b]);
+        });
+        lc.smem_per_warp = (int)smem_per_warp_bytes(lc.n_cap, ctx->TS, ctx->K1, ctx->KPL);
+        lc.warps = std::min(8, ctx->max_smem / lc.smem_per_warp);
+        if (lc.warps < 1)
+            return fail(ctx, STM_ERR_UNSUPPORTED,
+                        "a document's beta tile (" + std::to_string(lc.smem_per_warp) +
+                            " bytes) does not fit in shared memory");
+        lc.grid = std::min(ctx->sm_count, (lc.n_docs + lc.warps - 1) / lc.warps);
+        CU(cudaMalloc(&lc.d_docs, sizeof(int) * lc.n_docs));
+        CU(cudaMemcpy(lc.d_docs, members[ci].data(), sizeof(int) * lc.n_docs, cudaMemcpyHostToDevice));
+        max_warps = std::max(max_warps, lc.grid * lc.warps);
+        ctx->classes.push_back(lc);
+    }
+    CU(cudaMalloc(&ctx->d_doc_ptr, sizeof(long long) * (D + 1)));
+    CU(cudaMemcpy(ctx->d_doc_ptr, doc_ptr, sizeof(long long) * (D + 1), cudaMemcpyHostToDevice));
+    CU(cudaMalloc(&ctx->d_word_id, sizeof(int) * std::max<int64_t>(nnz, 1)));
+    CU(cudaMalloc(&ctx->d_count, sizeof(float) * std::max<int64_t>(nnz, 1)));
+    if (nnz) {
+        CU(cudaMemcpy(ctx->d_word_id, word_id, sizeof(int) * nnz, cudaMemcpyHostToDevice));
+        CU(cudaMemcpy(ctx->d_count, count, sizeof(float) * nnz, cudaMemcpyHostToDevice));
+    }
+    if (aspect) {
+        CU(cudaMalloc(&ctx->d_aspect, sizeof(int) * std::max<int64_t>(D, 1)));
+        CU(cudaMemcpy(ctx->d_aspect, aspect, sizeof(int) * D, cudaMemcpyHostToDevice));
+    }
+    CU(cudaMalloc(&ctx->d_queues, sizeof(unsigned int) * 16));
+    ctx->max_warps_total = std::max(max_warps, 1);
+    ctx->scratch_stride = 2LL * ctx->K1 * ctx->K1;
+    CU(cudaMalloc(&ctx->d_scratch, sizeof(double) * ctx->scratch_stride * ctx->max_warps_total));
+    ctx->n_rep = 16;
+    CU(cudaMalloc(&ctx->d_sigma_rep, sizeof(double) * ctx->n_rep * ctx->K1 * ctx->K1));
+    CU(cudaMalloc(&ctx->d_ones, sizeof(double) * std::max<int64_t>(D, 1)));
+    fill_kernel<<<256, 256>>>(ctx->d_ones, D, 1.0);
+    ctx->colsum_blocks = std::min(1024, (ctx->V + 63) / 64);
+    CU(cudaMalloc(&ctx->d_colsum_part, sizeof(double) * (size_t)ctx->colsum_blocks * ctx->TS));
+    CU(cudaDeviceSynchronize());
+    return STM_OK;
+}
+
+int stm_stats_layout(const stm_ctx* ctx, int p, int64_t* offsets) {
+    if (!ctx || !offsets || p < 0) return STM_ERR_INVALID;
+    layout(ctx, p, offsets);
+    return STM_OK;
+}
+
+int stm_prologue(stm_ctx* ctx, const double* sigma_dev, double* prior_dev, int* info_dev, void* stream) {
+    if (!ctx || !sigma_dev || !prior_dev || !info_dev) return STM_ERR_INVALID;
+    cudaStream_t st = (cudaStream_t)stream;
+    CU(cudaSetDevice(ctx->device));
+    const int K1 = ctx->K1;
+    double* L = ctx->d_msmall;  // K1*K1
+    CU(cudaMemcpyAsync(L, sigma_dev, sizeof(double) * K1 * K1, cudaMemcpyDeviceToDevice, st));
+    CS(cusolverDnSetStream(ctx->cusolver, st));
+    CS(cusolverDnDpotrf(ctx->cusolver, CUBLAS_FILL_MODE_LOWER, K1, L, K1, ctx->d_potrf_work, ctx->potrf_lwork, info_dev));
+    prior_from_chol_kernel<<<1, 32, 0, st>>>(L, K1, info_dev, prior_dev);
+    CU(cudaGetLastError());
+    return STM_OK;
+}
+
+int stm_estep(stm_ctx* ctx, const float* beta_t_dev, const double* mu_dev, const double* prior_dev,
+              double* eta_dev, double* theta_dev, double* stats_dev, double* doc_bound_dev,
+              int32_t* doc_info_dev, int32_t* doc_nfev_dev, void* stream) {
+    if (!ctx) return STM_ERR_INVALID;
+    if (!ctx->d_doc_ptr) return fail(ctx, STM_ERR_NO_CORPUS, "stm_set_corpus has not been called");
+    if (!beta_t_dev || !mu_dev || !prior_dev || !eta_dev || !theta_dev || !stats_dev || !doc_bound_dev ||
+        !doc_info_dev || !doc_nfev_dev)
+        return fail(ctx, STM_ERR_INVALID, "NULL device pointer passed to stm_estep");
+    cudaStream_t st = (cudaStream_t)stream;
+    CU(cudaSetDevice(ctx->device));
+    int64_t off[10];
+    layout(ctx, 0, off);
+    const int K1 = ctx->K1;
+    CU(cudaMemsetAsync(stats_dev + off[0], 0, sizeof(double) * (size_t)ctx->A * ctx->V * ctx->TS, st));
+    CU(cudaMemsetAsync(ctx->d_sigma_rep, 0, sizeof(double) * ctx->n_rep * K1 * K1, st));
+    CU(cudaMemsetAsync(ctx->d_queues, 0, sizeof(unsigned int) * 16, st));
+    int ci = 0;
+    for (const auto& lc : ctx->classes) {
+        stm::EstepParams P;
+        P.doc_ptr = ctx->d_doc_ptr; P.word_id = ctx->d_word_id; P.count = ctx->d_count; P.aspect = ctx->d_aspect;
+        P.docs = lc.d_docs; P.n_docs = lc.n_docs; P.queue = ctx->d_queues + ci;
+        P.K = ctx->K; P.V = ctx->V; P.A = ctx->A; P.TS = ctx->TS;
+        P.beta_t = beta_t_dev; P.mu = mu_dev; P.prior = prior_dev;
+        P.eta = eta_dev; P.theta = theta_dev; P.doc_bound = doc_bound_dev; P.doc_info = doc_info_dev;
+        P.doc_nfev = doc_nfev_dev;
+        P.beta_ss_t = stats_dev + off[0];
+        P.sigma_ss_rep = ctx->d_sigma_rep; P.n_rep = ctx->n_rep;
+        P.scratch = ctx->d_scratch; P.scratch_stride = ctx->scratch_stride;
+        P.n_cap = lc.n_cap; P.smem_per_warp = lc.smem_per_warp;
+        const size_t smem = (size_t)lc.smem_per_warp * lc.warps;
+        CU(launch_class(ctx->KPL, P, lc.J, lc.grid, lc.warps * 32, smem, st));
+        ctx->launches++;
+        ci++;
+    }
+    estep_epilogue_kernel<<<1, 1024, 0, st>>>(ctx->d_sigma_rep, ctx->n_rep, K1, doc_bound_dev, ctx->D,
+                                              stats_dev + off[1], stats_dev + off[2], stats_dev + off[3]);
+    CU(cudaGetLastError());
+    return STM_OK;
+}
+
+int stm_moments(stm_ctx* ctx, const double* eta_dev, const double* x_dev, int p, double* stats_dev, void* stream) {
+    if (!ctx || !eta_dev || !stats_dev || p < 0 || (p > 0 && !x_dev)) return STM_ERR_INVALID;
+    if (!ctx->d_doc_ptr) return fail(ctx, STM_ERR_NO_CORPUS, "stm_set_corpus has not been called");
+    cudaStream_t st = (cudaStream_t)stream;
+    CU(cudaSetDevice(ctx->device));
+    CB(cublasSetStream(ctx->cublas, st));
+    int64_t off[10];
+    layout(ctx, p, off);
+    const int K1 = ctx->K1;
+    const int D = (int)ctx->D;
+    const double one = 1.0, zero = 0.0;
+    if (D == 0) {
+        CU(cudaMemsetAsync(stats_dev + off[4], 0, sizeof(double) * (off[9] - off[4]), st));
+        return STM_OK;
+    }
+    // eta is row-major [D][K1] == column-major K1 x D (ld K1); X row-major [D][p] == column-major p x D
+    CB(cublasDgemv(ctx->cublas, CUBLAS_OP_N, K1, D, &one, eta_dev, K1, ctx->d_ones, 1, &zero, stats_dev + off[4], 1));
+    CB(cublasDgemm(ctx->cublas, CUBLAS_OP_N, CUBLAS_OP_T, K1, K1, D, &one, eta_dev, K1, eta_dev, K1, &zero,
+                   stats_dev + off[8], K1));
+    if (p > 0) {
+        CB(cublasDgemv(ctx->cublas, CUBLAS_OP_N, p, D, &one, x_dev, p, ctx->d_ones, 1, &zero, stats_dev + off[5], 1));
+        CB(cublasDgemm(ctx->cublas, CUBLAS_OP_N, CUBLAS_OP_T, p, p, D, &one, x_dev, p, x_dev, p, &zero,
+                       stats_dev + off[6], p));
+        // xte row-major [p][K1] == column-major K1 x p = eta' X'^T
+        CB(cublasDgemm(ctx->cublas, CUBLAS_OP_N, CUBLAS_OP_T, K1, p, D, &one, eta_dev, K1, x_dev, p, &zero,
+                       stats_dev + off[7], K1));
+    }
+    return STM_OK;
+}
+
+int stm_mstep(stm_ctx* ctx, const double* stats_dev, const double* x_dev, int p, int model, double sigprior,
+              double* gamma_t_dev, double* mu_dev, double* sigma_dev, float* beta_t_dev, double* beta64_t_dev,
+              void* stream) {
+    if (!ctx || !stats_dev || !mu_dev || !sigma_dev || !beta_t_dev) return STM_ERR_INVALID;
+    if (!(sigprior >= 0.0 && sigprior <= 1.0))
+        return fail(ctx, STM_ERR_INVALID, "weight needs to be defined between 0 and 1");  // stm.py:721
+    if (model != STM_MODEL_STM && model != STM_MODEL_CTM)
+        return fail(ctx, STM_ERR_INVALID, "Updating the topical prevalence parameter requires a mode");  // stm.py:709
+    if (model == STM_MODEL_STM && (p < 1 || !x_dev || !gamma_t_dev))
+        return fail(ctx, STM_ERR_INVALID, "STM mode needs a design matrix with p >= 1 and a gamma buffer");
+    cudaStream_t st = (cudaStream_t)stream;
+    CU(cudaSetDevice(ctx->device));
+    CB(cublasSetStream(ctx->cublas, st));
+    CS(cusolverDnSetStream(ctx->cusolver, st));
+    const int K1 = ctx->K1, K = ctx->K, V = ctx->V, TS = ctx->TS;
+    const int D = (int)ctx->D;
+    int64_t off[10];
+    layout(ctx, model == STM_MODEL_STM ? p : p, off);
+    // small workspace carve-up
+    const int64_t need = 16 + (int64_t)p * p + p + 3LL * p * K1 + 2LL * TS * ctx->A;
+    if (need > ctx->msmall_len) {
+        cudaFree(ctx->d_msmall);
+        ctx->msmall_len = need + 1024;
+        CU(cudaMalloc(&ctx->d_msmall, sizeof(double) * ctx->msmall_len));
+    }
+    long long* d_off = reinterpret_cast<long long*>(ctx->d_msmall);  // 10 offsets in the first 16 doubles
+    double* G = ctx->d_msmall + 16;
+    double* lam = G + (int64_t)p * p;
+    double* R = lam + p;
+    double* tmp = R + (int64_t)p * K1;
+    double* rowsum = tmp + (int64_t)p * K1;
+    long long hoff[10];
+    for (int i = 0; i < 10; ++i) hoff[i] = off[i];
+    CU(cudaMemcpyAsync(d_off, hoff, sizeof(hoff), cudaMemcpyHostToDevice, st));
+
+    // ---- update_mu ---------------------------------------------------------------------------
+    if (model == STM_MODEL_STM) {
+        center_moments_kernel<<<1, 256, 0, st>>>(stats_dev, d_off, p, K1, G, R);
+        if (ctx->syevd_p != p) {
+            int lwork = 0;
+            CS(cusolverDnDsyevd_bufferSize(ctx->cusolver, CUSOLVER_EIG_MODE_VECTOR, CUBLAS_FILL_MODE_LOWER, p, G, p,
+                                           lam, &lwork));
+            cudaFree(ctx->d_syevd_work);
+            ctx->syevd_lwork = std::max(lwork, 1);
+            CU(cudaMalloc(&ctx->d_syevd_work, sizeof(double) * ctx->syevd_lwork));
+            ctx->syevd_p = p;
+        }
+        CS(cusolverDnDsyevd(ctx->cusolver, CUSOLVER_EIG_MODE_VECTOR, CUBLAS_FILL_MODE_LOWER, p, G, p, lam,
+                            ctx->d_syevd_work, ctx->syevd_lwork, ctx->d_info + 1));
+        solve_gamma_kernel<<<1, 256, 0, st>>>(G, lam, R, p, K1, tmp, gamma_t_dev);
+        // mu (column-major K1 x D) = gamma_t (column-major K1 x p) * X (column-major p x D)
+        if (D > 0) {
+            const double one = 1.0, zero = 0.0;
+            CB(cublasDgemm(ctx->cublas, CUBLAS_OP_N, CUBLAS_OP_N, K1, D, p, &one, gamma_t_dev, K1, x_dev, p, &zero,
+                           mu_dev, K1));
+        }
+    } else {
+        mu_ctm_kernel<<<256, 256, 0, st>>>(stats_dev, d_off, K1, ctx->D, mu_dev);
+    }
+    // ---- update_sigma ------------------------------------------------------------------------
+    sigma_update_kernel<<<1, 256, 0, st>>>(stats_dev, d_off, p, K1, model, gamma_t_dev, sigprior, tmp, sigma_dev);
+    // ---- update_beta -------------------------------------------------------------------------
+    const double* ss = stats_dev + off[0];
+    if (ctx->A == 1) {
+        const int rows_per_block = (V + ctx->colsum_blocks - 1) / ctx->colsum_blocks;
+        const int nblk = (V + rows_per_block - 1) / rows_per_block;
+        colsum_partial_kernel<<<nblk, ((TS + 31) / 32) * 32, 0, st>>>(ss, V, TS, rows_per_block, ctx->d_colsum_part);
+        colsum_final_kernel<<<1, ((TS + 31) / 32) * 32, 0, st>>>(ctx->d_colsum_part, nblk, TS, rowsum);
+        beta_normalise_kernel<<<ctx->sm_count * 4, 256, 0, st>>>(ss, rowsum, V, K, TS, beta_t_dev, beta64_t_dev);
+    } else {
+        beta_normalise_aspect_kernel<<<ctx->sm_count * 4, 256, 0, st>>>(ss, (long long)ctx->A * V, K, TS, beta_t_dev,
+                                                                        beta64_t_dev);
+    }
+    CU(cudaGetLastError());
+    return STM_OK;
+}
+
+int stm_beta_to_wordmajor(stm_ctx* ctx, const double* beta_kv_dev, float* beta_t_dev, void* stream) {
+    if (!ctx || !beta_kv_dev || !beta_t_dev) return STM_ERR_INVALID;
+    CU(cudaSetDevice(ctx->device));
+    beta_to_wordmajor_kernel<<<ctx->sm_count * 4, 256, 0, (cudaStream_t)stream>>>(beta_kv_dev, beta_t_dev, ctx->A,
+                                                                                  ctx->K, ctx->V, ctx->TS);
+    CU(cudaGetLastError());
+    return STM_OK;
+}
+int stm_wordmajor_to_kv(stm_ctx* ctx, const double* src_t_dev, double* dst_kv_dev, void* stream) {
+    if (!ctx || !src_t_dev || !dst_kv_dev) return STM_ERR_INVALID;
+    CU(cudaSetDevice(ctx->device));
+    wordmajor_to_kv_kernel<<<ctx->sm_count * 4, 256, 0, (cudaStream_t)stream>>>(src_t_dev, dst_kv_dev, ctx->A, ctx->K,
+                                                                                ctx->V, ctx->TS);
+    CU(cudaGetLastError());
+    return STM_OK;
+}
+
+int stm_estep_host(stm_ctx* ctx, const double* beta, const double* mu, const double* siginv, double sigmaentropy,
+                   double* eta, double* theta, double* beta_ss, double* sigma_ss, double* bound, double* doc_bound,
+                   int32_t* doc_status, int32_t* doc_nit, int32_t* doc_repair) {
+    if (!ctx) return STM_ERR_INVALID;
+    if (!ctx->d_doc_ptr) return fail(ctx, STM_ERR_NO_CORPUS, "stm_set_corpus has not been called");
+    if (!beta || !mu || !siginv || !eta || !theta || !beta_ss || !sigma_ss || !bound)
+        return fail(ctx, STM_ERR_INVALID, "NULL host pointer passed to stm_estep_host");
+    CU(cudaSetDevice(ctx->device));
+    const int K = ctx->K, K1 = ctx->K1, V = ctx->V, A = ctx->A, TS = ctx->TS;
+    const int64_t D = ctx->D;
+    // the reference's siginv is diagonal by construction (stm.py:501); anything else is not this path
+    std::vector<double> prior(K1 + 1);
+    for (int i = 0; i < K1; ++i)
+        for (int j = 0; j < K1; ++j) {
+            const double s = siginv[(size_t)i * K1 + j];
+            if (i == j) prior[i] = s;
+            else if (s != 0.0)
+                return fail(ctx, STM_ERR_UNSUPPORTED, "siginv must be diagonal (as produced by stm.py:501)");
+        }
+    prior[K1] = sigmaentropy;
+    int64_t off[10];
+    layout(ctx, 0, off);
+    if (!ctx->host_bufs) {
+        const size_t akv = (size_t)A * K * V;
+        CU(cudaMalloc(&ctx->h_beta_kv, sizeof(double) * akv));
+        CU(cudaMalloc(&ctx->h_bss_kv, sizeof(double) * akv));
+        CU(cudaMalloc(&ctx->h_beta_t, sizeof(float) * (size_t)A * V * TS));
+        CU(cudaMalloc(&ctx->h_mu, sizeof(double) * std::max<int64_t>(D * K1, 1)));
+        CU(cudaMalloc(&ctx->h_eta, sizeof(double) * std::max<int64_t>(D * K1, 1)));
+        CU(cudaMalloc(&ctx->h_theta, sizeof(double) * std::max<int64_t>(D * K, 1)));
+        CU(cudaMalloc(&ctx->h_stats, sizeof(double) * off[9]));
+        CU(cudaMalloc(&ctx->h_prior, sizeof(double) * (K1 + 1)));
+        CU(cudaMalloc(&ctx->h_doc_bound, sizeof(double) * std::max<int64_t>(D, 1)));
+        CU(cudaMalloc(&ctx->h_doc_info, sizeof(int32_t) * std::max<int64_t>(3 * D, 1)));
+        CU(cudaMalloc(&ctx->h_doc_nfev, sizeof(int32_t) * std::max<int64_t>(D, 1)));
+        ctx->host_bufs = true;
+    }
+    cudaStream_t st = 0;
+    CU(cudaMemcpyAsync(ctx->h_beta_kv, beta, sizeof(double) * (size_t)A * K * V, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(ctx->h_mu, mu, sizeof(double) * D * K1, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(ctx->h_eta, eta, sizeof(double) * D * K1, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(ctx->h_prior, prior.data(), sizeof(double) * (K1 + 1), cudaMemcpyHostToDevice, st));
+    int rc = stm_beta_to_wordmajor(ctx, ctx->h_beta_kv, ctx->h_beta_t, st);
+    if (rc) return rc;
+    rc = stm_estep(ctx, ctx->h_beta_t, ctx->h_mu, ctx->h_prior, ctx->h_eta, ctx->h_theta, ctx->h_stats,
+                   ctx->h_doc_bound, ctx->h_doc_info, ctx->h_doc_nfev, st);
+    if (rc) return rc;
+    rc = stm_wordmajor_to_kv(ctx, ctx->h_stats + off[0], ctx->h_bss_kv, st);
+    if (rc) return rc;
+    CU(cudaMemcpyAsync(eta, ctx->h_eta, sizeof(double) * D * K1, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(theta, ctx->h_theta, sizeof(double) * D * K, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(beta_ss, ctx->h_bss_kv, sizeof(double) * (size_t)A * K * V, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(sigma_ss, ctx->h_stats + off[1], sizeof(double) * K1 * K1, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(bound, ctx->h_stats + off[2], sizeof(double), cudaMemcpyDeviceToHost, st));
+    if (doc_bound) CU(cudaMemcpyAsync(doc_bound, ctx->h_doc_bound, sizeof(double) * D, cudaMemcpyDeviceToHost, st));
+    if (doc_status || doc_nit || doc_repair) {
+        int32_t* u = ctx->h_doc_info;  // [3][D]: reuse the tail as unpack space (info itself is read first)
+        int32_t* st_d = u + D;         // status -> second third, nit/repair share: unpack per request
+        // unpack into two spare thirds, copying each requested field out
+        if (doc_status) {
+            unpack_info_kernel<<<256, 256, 0, st>>>(ctx->h_doc_info, D, st_d, nullptr, nullptr);
+            CU(cudaMemcpyAsync(doc_status, st_d, sizeof(int32_t) * D, cudaMemcpyDeviceToHost, st));
+        }
+        if (doc_nit) {
+            unpack_info_kernel<<<256, 256, 0, st>>>(ctx->h_doc_info, D, nullptr, u + 2 * D, nullptr);
+            CU(cudaMemcpyAsync(doc_nit, u + 2 * D, sizeof(int32_t) * D, cudaMemcpyDeviceToHost, st));
+        }
+        if (doc_repair) {
+            CU(cudaStreamSynchronize(st));
+            unpack_info_kernel<<<256, 256, 0, st>>>(ctx->h_doc_info, D, nullptr, nullptr, st_d);
+            CU(cudaMemcpyAsync(doc_repair, st_d, sizeof(int32_t) * D, cudaMemcpyDeviceToHost, st));
+        }
+    }
+    CU(cudaStreamSynchronize(st));
+    return STM_OK;
+}
+
+}  // extern "C"
