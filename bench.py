@@ -1,0 +1,399 @@
+#!/usr/bin/env python
+"""bench.py — E-step docs/sec at K=50, V=10k (BASELINE.json metric) on synthetic corpora.
+
+    python bench.py --gpus N --steps K --warmup W            # our CUDA path
+    python bench.py --impl reference --gpus N --steps K ...  # the reference's NumPy/SciPy path on host cores
+
+Workload (config.workload): BASELINE.json configs[2]/[3] — D=100k documents per GPU, V=10k, K=50,
+150 tokens/doc from the reference's DGP (generate_docs.py:180-316), random init, 1 prevalence
+covariate.  A "step" is ONE EM iteration (E-step kernel + moments + the one all-reduce + M-step)
+over the resident corpus; `value` = documents processed by all ranks / max-over-ranks device time.
+`e2e` = the same documents through the reference-facing host call stm_estep_host (fp64 host
+buffers in the reference's layouts, H2D + D2H inside the timed region).
+Prints ONE JSON line on rank 0.
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "estep_docs_per_sec_K50_V10k"
+UNIT = "docs/s"
+
+
+def make_corpus(D, V, K, n_words=150, seed=12345, p=1):
+    """Vectorised sampler with the reference DGP's distributions (generate_docs.py:180-316):
+    beta_k ~ Dir(0.05), X ~ U{0,1}, eta ~ N(X gamma', 0.001 I), theta = softmax([eta, 0]),
+    doc ~ Multinomial(n_words, theta beta) drawn as topic-then-word.  -> CSR + X."""
+    rng = np.random.default_rng(seed)
+    beta = rng.dirichlet(np.full(V, 0.05), K)
+    cum = np.cumsum(beta, axis=1)
+    cum[:, -1] = 1.0
+    rng = np.random.default_rng(seed + 1000003 * (1 + int(os.environ.get("RANK", "0"))))
+    X = rng.integers(0, 2, size=(D, p)).astype(np.float64)
+    gamma = np.random.default_rng(seed + 7).normal(0.0, 1.0, size=(K - 1, p))
+    eta = X @ gamma.T + rng.normal(0, np.sqrt(0.001), size=(D, K - 1))
+    full = np.concatenate([eta, np.zeros((D, 1))], axis=1)
+    theta = np.exp(full - full.max(1, keepdims=True))
+    theta /= theta.sum(1, keepdims=True)
+    tc = np.cumsum(theta, axis=1)
+    tc[:, -1] = 1.0
+    u = rng.random((D, n_words))
+    z = (u[:, :, None] > tc[:, None, :]).sum(axis=2).astype(np.int32) if K <= 8 else None
+    if z is None:
+        z = np.empty((D, n_words), dtype=np.int32)
+        for lo in range(0, D, 8192):
+            hi = min(D, lo + 8192)
+            z[lo:hi] = (u[lo:hi, :, None] > tc[lo:hi, None, :]).sum(axis=2)
+    np.minimum(z, K - 1, out=z)
+    u2 = rng.random((D, n_words))
+    w = np.empty((D, n_words), dtype=np.int64)
+    zf, wf, uf = z.reshape(-1), w.reshape(-1), u2.reshape(-1)
+    for k in range(K):
+        sel = np.nonzero(zf == k)[0]
+        wf[sel] = np.searchsorted(cum[k], uf[sel], side="left")
+    np.minimum(wf, V - 1, out=wf)
+    key = (np.repeat(np.arange(D, dtype=np.int64), n_words) * V + wf)
+    uk, cnt = np.unique(key, return_counts=True)
+    doc = uk // V
+    ids = (uk % V).astype(np.int32)
+    ptr = np.zeros(D + 1, dtype=np.int64)
+    np.cumsum(np.bincount(doc, minlength=D), out=ptr[1:])
+    return ptr, ids, cnt.astype(np.float32), X
+
+
+def random_beta(K, V, seed=123456):
+    """the reference's random init (stm.py:425-429) with its legacy-RNG seed"""
+    rs = np.random.RandomState(seed)
+    b = rs.gamma(0.1, 1, V * K).reshape(K, V)
+    return b / b.sum(axis=1, keepdims=True)
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock + throttle reasons through NVML during the timed region."""
+
+    def __init__(self, device):
+        super().__init__(daemon=True)
+        self.device, self.samples, self.reasons, self.max_mhz = device, [], set(), None
+        self._stop_evt = threading.Event()
+        self.ok = False
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(device)
+            self.max_mhz = int(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            self.ok = True
+        except Exception:
+            self.ok = False
+
+    def run(self):
+        if not self.ok:
+            return
+        nv = self.nv
+        names = {
+            getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0x8): "hw_slowdown",
+            getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40): "hw_thermal_slowdown",
+            getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20): "sw_thermal_slowdown",
+            getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0x4): "sw_power_cap",
+        }
+        while not self._stop_evt.is_set():
+            try:
+                self.samples.append(int(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+                r = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
+                for bit, name in names.items():
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            self._stop_evt.wait(0.05)
+
+    def stop(self):
+        self._stop_evt.set()
+        self.join(timeout=2)
+        med = int(np.median(self.samples)) if self.samples else None
+        return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
+
+
+# ----------------------------------------------------------------------------------------------------
+# reference arm: the reference's NumPy/SciPy E-step (oracle/stm_numpy.py, bit-identical to
+# /root/reference/src/modules/stm.py on the golden fixtures) on all host cores
+# ----------------------------------------------------------------------------------------------------
+def _ref_worker(args):
+    from oracle import stm_numpy
+    ptr, ids, cnt, beta, mu, siginv, ent, eta0 = args
+    t = time.perf_counter()
+    o = stm_numpy.estep(ptr, ids, cnt, beta, mu, siginv, ent, eta0)
+    return time.perf_counter() - t, o["bound"], o["eta"]
+
+
+def slice_csr(ptr, ids, cnt, sel):
+    lens = ptr[sel + 1] - ptr[sel]
+    p = np.zeros(len(sel) + 1, dtype=np.int64)
+    np.cumsum(lens, out=p[1:])
+    idx = np.concatenate([np.arange(ptr[d], ptr[d + 1]) for d in sel]) if len(sel) else np.zeros(0, np.int64)
+    return p, ids[idx], cnt[idx].astype(np.float64)
+
+
+def run_numpy_port(ptr, ids, cnt, beta, mu, siginv, ent, eta0, sel, nproc):
+    """E-step of the NumPy/SciPy port on documents `sel`, split over nproc processes.
+    -> (wall seconds, bound, eta[sel])"""
+    import multiprocessing as mp
+    chunks = [c for c in np.array_split(np.asarray(sel), nproc) if len(c)]
+    jobs = []
+    for c in chunks:
+        p, i, w = slice_csr(ptr, ids, cnt, c)
+        jobs.append((p, i, w, beta, mu[c], siginv, ent, eta0[c]))
+    ctx = mp.get_context("fork")
+    t = time.perf_counter()
+    with ctx.Pool(len(jobs)) as pool:
+        res = pool.map(_ref_worker, jobs)
+    wall = time.perf_counter() - t
+    return wall, float(sum(r[1] for r in res)), np.concatenate([r[2] for r in res], axis=0)
+
+
+def reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import stm_numpy
+    nproc = os.cpu_count() or 1
+    K, V = args.K, args.V
+    per = args.ref_docs_per_core
+    D = per * nproc
+    ptr, ids, cnt, X = make_corpus(D, V, K, seed=args.seed)
+    beta = random_beta(K, V)
+    siginv, ent = stm_numpy.prologue(np.eye(K - 1) * 20.0)
+    mu = np.zeros((D, K - 1))
+    eta0 = np.zeros((D, K - 1))
+    sel = np.arange(D)
+    for _ in range(args.warmup):
+        run_numpy_port(ptr, ids, cnt, beta, mu, siginv, ent, eta0, sel[:nproc * 2], nproc)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        run_numpy_port(ptr, ids, cnt, beta, mu, siginv, ent, eta0, sel, nproc)
+    wall = time.perf_counter() - t0
+    value = D * args.steps / wall
+    sample = (f"{D} documents/step ({per} per core) of the same synthetic workload at the reference's initial "
+              f"state (eta=0, mu=0, Sigma=20 I, random init), NumPy/SciPy E-step (oracle/stm_numpy.py) in {nproc} processes")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * wall / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"C3: D=100k/GPU V={V} K={K}, 150 tokens/doc (bounded sample of {D} docs/step)"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": nproc, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------------------------------
+# our arm
+# ----------------------------------------------------------------------------------------------------
+def ours(args):
+    import torch
+    import torch.distributed as dist
+    from strutopy_b200 import STM, _lib
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a CUDA device; there is no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    dev = torch.device("cuda", local_rank)
+
+    K, V, D = args.K, args.V, args.docs
+    if args.scaling == "strong":
+        D = (D + world - 1) // world
+    ptr, ids, cnt, X = make_corpus(D, V, K, seed=args.seed)
+    mean_nd = float(ptr[-1]) / D
+    model = STM((ptr, ids, cnt), range(V), False, K, X, False, 10 ** 9, 0, 0.0, init_type="random",
+                model_type="STM", device=local_rank, distributed=(world > 1), presharded=True)
+    model.beta = random_beta(K, V)
+    L, h = _lib.load(), model._ctx.handle
+
+    def em_iteration(events=None):
+        if events is not None:
+            events[0].record()
+        model._estep_device()
+        if events is not None:
+            events[1].record()
+        bound = model._reduce_and_bound()
+        model._mstep_device()
+        return bound
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # L2 hygiene: the per-step working set (eta, mu, theta, beta_ss, corpus: > 250 MB) exceeds the 126 MB L2
+    bounds = []
+    for _ in range(args.warmup):
+        bounds.append(em_iteration())
+    # snapshot for the parity / e2e / cpu legs: the state the first timed E-step starts from
+    snap = dict(beta=model.beta.copy(), mu=model._d["mu"].cpu().numpy(), sigma=model.sigma.copy(),
+                eta0=model._d["eta"].cpu().numpy())
+
+    sampler = ClockSampler(local_rank)
+    ev = [[torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)] for _ in range(args.steps)]
+    l0 = model._ctx.launch_count()
+    barrier()
+    sampler.start()
+    t_start = torch.cuda.Event(enable_timing=True)
+    t_end = torch.cuda.Event(enable_timing=True)
+    t_start.record()
+    for s in range(args.steps):
+        bounds.append(em_iteration(ev[s]))
+    t_end.record()
+    barrier()
+    clocks = sampler.stop()
+    launches = model._ctx.launch_count() - l0
+    ms_total = t_start.elapsed_time(t_end)
+    estep_ms = [a.elapsed_time(b) for a, b in ev]
+    tt = torch.tensor([ms_total, float(np.mean(estep_ms))], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    ms_total, estep_ms_mean = float(tt[0]), float(tt[1])
+    docs_total = D * world
+    value = docs_total * args.steps / (ms_total * 1e-3)
+
+    # ---- e2e: the reference-facing host call (stm_estep_host) with pinned fp64 host buffers ----------
+    K1 = K - 1
+    from oracle import stm_numpy  # checker / CPU baseline only (never on the measured path)
+    siginv, ent = stm_numpy.prologue(snap["sigma"])
+    pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory()  # noqa: E731
+    hb = dict(beta=pin(snap["beta"]), mu=pin(snap["mu"]), siginv=pin(siginv), eta=pin(snap["eta0"]),
+              theta=torch.empty((D, K), dtype=torch.float64).pin_memory(),
+              bss=torch.empty((K, V), dtype=torch.float64).pin_memory(),
+              sss=torch.empty((K1, K1), dtype=torch.float64).pin_memory(),
+              bound=torch.zeros(1, dtype=torch.float64).pin_memory())
+    eta_in = pin(snap["eta0"])
+    vp = lambda t: t.data_ptr()  # noqa: E731
+
+    def host_call():
+        hb["eta"].copy_(eta_in)
+        _lib.check(h, L.stm_estep_host(h, vp(hb["beta"]), vp(hb["mu"]), vp(hb["siginv"]), float(ent), vp(hb["eta"]),
+                                       vp(hb["theta"]), vp(hb["bss"]), vp(hb["sss"]), vp(hb["bound"]),
+                                       None, None, None, None))
+
+    for _ in range(min(args.warmup, 3)):
+        host_call()
+    barrier()
+    e_start = torch.cuda.Event(enable_timing=True)
+    e_end = torch.cuda.Event(enable_timing=True)
+    t0 = time.perf_counter()
+    e_start.record()
+    for _ in range(args.steps):
+        host_call()
+    e_end.record()
+    barrier()
+    e2e_s = max(time.perf_counter() - t0, e_start.elapsed_time(e_end) * 1e-3)
+    te = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_value = docs_total * args.steps / float(te[0])
+    h2d = 8 * (K * V + 2 * D * K1 + K1 + 1)
+    d2h = 8 * (D * K1 + D * K + K * V + K1 * K1 + 1)
+    gpu_bound_snap = float(hb["bound"][0])
+    gpu_eta_snap = hb["eta"].numpy().copy()
+
+    line = None
+    if rank == 0:
+        # ---- roofline of the dominant kernel (the E-step kernel) --------------------------------------
+        peaks = {}
+        try:
+            with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+                peaks = json.load(f)
+        except Exception:
+            pass
+        peak = float(peaks.get("hbm_gbs", 6650.0))
+        b_doc = mean_nd * (8 + 8 * K) + 16 * K - 4            # SURVEY.md §8d algorithmic bytes / document
+        achieved = b_doc * D / (estep_ms_mean * 1e-3) / 1e9   # GB/s, per launch (this rank's D documents)
+        traffic = None
+        try:
+            with open(os.path.join(ROOT, "profiles", "estep_dram_traffic.json")) as f:
+                traffic = json.load(f).get("dram_bytes_per_launch")
+        except Exception:
+            pass
+        # ---- CPU baseline + parity on a bounded sample (rank 0, N=1 only) --------------------------------
+        cpu = None
+        parity = None
+        if world == 1 and not args.no_cpu:
+            nproc = os.cpu_count() or 1
+            n_s = min(D, args.ref_docs_per_core * nproc)
+            sel = np.sort(np.random.default_rng(5).choice(D, size=n_s, replace=False))
+            beta32 = snap["beta"].astype(np.float32).astype(np.float64)
+            wall, b_ref, eta_ref = run_numpy_port(ptr, ids, cnt, beta32, snap["mu"], siginv, ent, snap["eta0"], sel, nproc)
+            cpu = {"value": n_s / wall, "unit": UNIT, "cores": nproc, "kind": "port",
+                   "sample": f"{n_s} random documents of the same corpus and state as the first timed E-step; "
+                             f"NumPy/SciPy E-step (oracle/stm_numpy.py == reference arithmetic) in {nproc} processes"}
+            # parity of the CUDA path on the same documents (same snapshot state)
+            db = model.doc_diagnostics()  # (state has moved on; recompute through the host call result)
+            del db
+            from oracle import c_oracle
+            o = c_oracle.estep(ptr, ids, cnt, beta32, snap["mu"], siginv, ent, snap["eta0"], nthreads=nproc)
+            parity = {
+                "elbo_rel_err_vs_c_oracle_full": abs(gpu_bound_snap - o["bound"]) / abs(o["bound"]),
+                "max_abs_eta_err_vs_c_oracle_full": float(np.abs(gpu_eta_snap - o["eta"]).max()),
+                "max_abs_eta_err_vs_numpy_port_sample": float(np.abs(gpu_eta_snap[sel] - eta_ref).max()),
+                "c_oracle_docs_per_sec": None,
+            }
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True,
+            "scaling": args.scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"C3: D={D}/GPU V={V} K={K}, 150 tokens/doc (mean n_d {mean_nd:.1f}), "
+                                   "reference DGP, random init, 1 prevalence covariate; step = one EM iteration",
+                       "docs_per_gpu": D, "V": V, "K": K, "beta_storage": "fp32", "arithmetic": "fp64",
+                       "l2": "per-step working set (eta, mu, theta, corpus, beta_ss) > 250 MB exceeds the 126 MB L2",
+                       "parallelism": f"dp{world}: documents sharded, one NCCL all-reduce of the packed statistics per step"},
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": traffic, "kernel": "stm::estep_kernel", "bytes_per_doc": b_doc,
+                         "estep_ms_per_launch": estep_ms_mean,
+                         "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s"},
+            "cpu_baseline": cpu,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "api": "stm_estep_host (C ABI, fp64 host buffers in the reference's layouts; corpus resident)"},
+            "gpu_launches": int(launches), "clocks": clocks,
+            "elbo_trace_tail": bounds[-3:], "parity": parity,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
+    ap.add_argument("--docs", type=int, default=100000, help="documents per GPU (weak) or in total (strong)")
+    ap.add_argument("--K", type=int, default=50)
+    ap.add_argument("--V", type=int, default=10000)
+    ap.add_argument("--seed", type=int, default=12345)
+    ap.add_argument("--ref-docs-per-core", type=int, default=48)
+    ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline / parity legs")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        reference_arm(args)
+    else:
+        ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -48,7 +48,8 @@ void stm_destroy(stm_ctx* ctx);
 const char* stm_last_error(const stm_ctx* ctx);
 /* word-major beta row stride in elements: smallest multiple of 4 >= K whose quarter is odd */
 int stm_beta_stride(int K);
-/* number of E-step kernel launches issued so far on this context (bench.py's gpu_launches) */
+/* number of this library's own kernel launches issued so far on this context (bench.py's
+ * gpu_launches; cuBLAS/cuSOLVER kernels are not counted) */
 int64_t stm_launch_count(const stm_ctx* ctx);
 
 /* ---- corpus ------------------------------------------------------------------------------------ */

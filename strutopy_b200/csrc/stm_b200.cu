@@ -553,6 +553,7 @@ int stm_prologue(stm_ctx* ctx, const double* sigma_dev, double* prior_dev, int* 
     CS(cusolverDnSetStream(ctx->cusolver, st));
     CS(cusolverDnDpotrf(ctx->cusolver, CUBLAS_FILL_MODE_LOWER, K1, L, K1, ctx->d_potrf_work, ctx->potrf_lwork, info_dev));
     prior_from_chol_kernel<<<1, 32, 0, st>>>(L, K1, info_dev, prior_dev);
+    ctx->launches++;
     CU(cudaGetLastError());
     return STM_OK;
 }
@@ -593,6 +594,7 @@ int stm_estep(stm_ctx* ctx, const float* beta_t_dev, const double* mu_dev, const
     }
     estep_epilogue_kernel<<<1, 1024, 0, st>>>(ctx->d_sigma_rep, ctx->n_rep, K1, doc_bound_dev, ctx->D,
                                               stats_dev + off[1], stats_dev + off[2], stats_dev + off[3]);
+    ctx->launches++;
     CU(cudaGetLastError());
     return STM_OK;
 }
@@ -677,6 +679,7 @@ int stm_mstep(stm_ctx* ctx, const double* stats_dev, const double* x_dev, int p,
         CS(cusolverDnDsyevd(ctx->cusolver, CUSOLVER_EIG_MODE_VECTOR, CUBLAS_FILL_MODE_LOWER, p, G, p, lam,
                             ctx->d_syevd_work, ctx->syevd_lwork, ctx->d_info + 1));
         solve_gamma_kernel<<<1, 256, 0, st>>>(G, lam, R, p, K1, tmp, gamma_t_dev);
+        ctx->launches += 2;
         // mu (column-major K1 x D) = gamma_t (column-major K1 x p) * X (column-major p x D)
         if (D > 0) {
             const double one = 1.0, zero = 0.0;
@@ -685,9 +688,11 @@ int stm_mstep(stm_ctx* ctx, const double* stats_dev, const double* x_dev, int p,
         }
     } else {
         mu_ctm_kernel<<<256, 256, 0, st>>>(stats_dev, d_off, K1, ctx->D, mu_dev);
+        ctx->launches++;
     }
     // ---- update_sigma ------------------------------------------------------------------------
     sigma_update_kernel<<<1, 256, 0, st>>>(stats_dev, d_off, p, K1, model, gamma_t_dev, sigprior, tmp, sigma_dev);
+    ctx->launches++;
     // ---- update_beta -------------------------------------------------------------------------
     const double* ss = stats_dev + off[0];
     if (ctx->A == 1) {
@@ -696,9 +701,11 @@ int stm_mstep(stm_ctx* ctx, const double* stats_dev, const double* x_dev, int p,
         colsum_partial_kernel<<<nblk, ((TS + 31) / 32) * 32, 0, st>>>(ss, V, TS, rows_per_block, ctx->d_colsum_part);
         colsum_final_kernel<<<1, ((TS + 31) / 32) * 32, 0, st>>>(ctx->d_colsum_part, nblk, TS, rowsum);
         beta_normalise_kernel<<<ctx->sm_count * 4, 256, 0, st>>>(ss, rowsum, V, K, TS, beta_t_dev, beta64_t_dev);
+        ctx->launches += 3;
     } else {
         beta_normalise_aspect_kernel<<<ctx->sm_count * 4, 256, 0, st>>>(ss, (long long)ctx->A * V, K, TS, beta_t_dev,
                                                                         beta64_t_dev);
+        ctx->launches++;
     }
     CU(cudaGetLastError());
     return STM_OK;
@@ -709,6 +716,7 @@ int stm_beta_to_wordmajor(stm_ctx* ctx, const double* beta_kv_dev, float* beta_t
     CU(cudaSetDevice(ctx->device));
     beta_to_wordmajor_kernel<<<ctx->sm_count * 4, 256, 0, (cudaStream_t)stream>>>(beta_kv_dev, beta_t_dev, ctx->A,
                                                                                   ctx->K, ctx->V, ctx->TS);
+    ctx->launches++;
     CU(cudaGetLastError());
     return STM_OK;
 }
@@ -717,6 +725,7 @@ int stm_wordmajor_to_kv(stm_ctx* ctx, const double* src_t_dev, double* dst_kv_de
     CU(cudaSetDevice(ctx->device));
     wordmajor_to_kv_kernel<<<ctx->sm_count * 4, 256, 0, (cudaStream_t)stream>>>(src_t_dev, dst_kv_dev, ctx->A, ctx->K,
                                                                                 ctx->V, ctx->TS);
+    ctx->launches++;
     CU(cudaGetLastError());
     return STM_OK;
 }

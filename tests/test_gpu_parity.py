@@ -1,0 +1,322 @@
+"""GPU parity tests (run on the B200 box with `-m gpu`): the CUDA path, called through the C ABI
+(libstm_b200.so via ctypes), against (a) fixtures generated from the live reference, (b) the
+reference's shipped known-answer ELBOs, (c) the C oracle on seeded synthetic corpora, and (d)
+size-independent invariants at BASELINE.json's full size (D=100k, V=10k, K=50).
+
+Tolerances (DESIGN.md "Tolerances"): beta is stored in fp32 on the device, all arithmetic is fp64.
+  * fixtures whose beta is fp32-representable: per-document eta <= 1e-6 abs (observed <= 1e-8),
+    ELBO <= 1e-9 rel (observed <= 1e-13), BFGS status / nit / PD-repair stage EQUAL;
+  * fp64 beta rounded to fp32 on upload: ELBO <= 1e-6 rel for one E-step;
+  * EM traces: <= 1e-4 rel per iteration (north-star tolerance; the reference's EM map amplifies
+    perturbations ~4x per iteration, see tests/test_oracle_golden.py::test_em_c1_trace_c_oracle).
+"""
+import numpy as np
+import pytest
+
+from conftest import load_golden, random_init_beta, synthetic_corpus
+from oracle import c_oracle, stm_numpy
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def lib():
+    import torch
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    from strutopy_b200 import _lib
+    _lib.load()
+    return _lib
+
+
+def _gpu_estep(lib, g, pfx, aspect=None):
+    K, V = int(g["K"]), int(g["V"])
+    A = int(g["A"]) if "A" in g else 1
+    ctx = lib.Context(K, V, A)
+    ctx.set_corpus(g["doc_ptr"], g["word_id"], g["count"], aspect)
+    o = ctx.estep_host(g[pfx + "beta"].astype(np.float64), g[pfx + "mu"], g[pfx + "siginv"],
+                       float(g[pfx + "sigmaentropy"]), g[pfx + "eta0"])
+    ctx.close()
+    return o
+
+
+def _assert_estep(o, g, pfx, eta_tol=1e-6, rel=1e-9):
+    assert np.abs(o["eta"] - g[pfx + "eta"]).max() <= eta_tol
+    assert np.abs(o["theta"] - g[pfx + "theta"]).max() <= eta_tol
+    assert abs(o["bound"] - g[pfx + "bound"]) <= rel * abs(g[pfx + "bound"])
+    np.testing.assert_allclose(o["doc_bound"], g[pfx + "doc_bound"], rtol=1e-7, atol=1e-6)
+    np.testing.assert_array_equal(o["status"], g[pfx + "status"])
+    np.testing.assert_array_equal(o["nit"], g[pfx + "nit"])
+    np.testing.assert_allclose(o["beta_ss"], g[pfx + "beta_ss"], rtol=0, atol=1e-6)
+    np.testing.assert_allclose(o["sigma_ss"], g[pfx + "sigma_ss"], rtol=1e-7, atol=1e-7)
+
+
+@pytest.mark.parametrize("name,its", [("estep_K5.npz", (0, 2)), ("estep_K20.npz", (0, 1)),
+                                      ("estep_K50.npz", (0, 1))])
+def test_estep_vs_live_reference_fixture(lib, name, its):
+    g = load_golden(name)
+    for it in its:
+        _assert_estep(_gpu_estep(lib, g, f"it{it}_"), g, f"it{it}_")
+
+
+def test_estep_content_aspects(lib):
+    g = load_golden("estep_content.npz")
+    _assert_estep(_gpu_estep(lib, g, "it0_", aspect=g["aspect"]), g, "it0_")
+
+
+def test_kat_small_fp64_beta(lib):
+    """SURVEY Appendix B known-answer vector; beta there is not fp32-representable."""
+    g = load_golden("kat_small.npz")
+    o = _gpu_estep(lib, g, "it0_")
+    assert abs(o["bound"] - (-25.70729258012203)) <= 1e-6 * 25.7
+    np.testing.assert_allclose(o["eta"], g["it0_eta"], atol=1e-6)
+    np.testing.assert_array_equal(o["nit"], g["it0_nit"])
+
+
+@pytest.mark.parametrize("K", [50, 70])
+def test_wiki_shipped_known_answer(lib, K):
+    """The reference's SHIPPED lower_bound.pickle[0] (K=50: -855111.024384962) on its shipped corpus."""
+    g = load_golden("wiki_corpus.npz")
+    V = int(g["V"])
+    D = len(g["doc_ptr"]) - 1
+    beta = random_init_beta(K, V)
+    siginv, ent = c_oracle.prologue(np.eye(K - 1) * 20.0)
+    ctx = lib.Context(K, V, 1)
+    ctx.set_corpus(g["doc_ptr"], g["word_id"], g["count"].astype(np.float32))
+    o = ctx.estep_host(beta, np.zeros((D, K - 1)), siginv, ent, np.zeros((D, K - 1)))
+    ctx.close()
+    shipped = g[f"shipped_bounds_{K}"][0]
+    assert abs(o["bound"] - shipped) <= 1e-6 * abs(shipped), (o["bound"], shipped)
+    assert (o["status"] == 2).mean() > 0.9  # the reference's normal exit: line-search failure
+    # and against the oracle fed the same fp32-rounded beta: tight
+    ref = c_oracle.estep(g["doc_ptr"], g["word_id"], g["count"].astype(np.float64),
+                         beta.astype(np.float32).astype(np.float64), np.zeros((D, K - 1)), siginv, ent,
+                         np.zeros((D, K - 1)), nthreads=4)
+    assert abs(o["bound"] - ref["bound"]) <= 1e-10 * abs(ref["bound"])
+    assert (np.abs(o["eta"] - ref["eta"]).max(axis=1) > 1e-6).mean() <= 0.002
+    np.testing.assert_array_equal(o["repair"], ref["repair"])
+
+
+@pytest.mark.parametrize("D,V,K,nw", [(1500, 1500, 8, 60), (1200, 3000, 33, 150), (600, 2500, 70, 150),
+                                      (400, 2000, 100, 200), (300, 2000, 128, 120)])
+def test_estep_vs_c_oracle_shapes(lib, D, V, K, nw):
+    """every KPL instantiation (K <= 32, 64, 96, 128) and several length classes"""
+    ptr, ids, cnt, X, _ = synthetic_corpus(D, V, K, n_words=nw, seed=K)
+    beta = random_init_beta(K, V).astype(np.float32).astype(np.float64)
+    rng = np.random.default_rng(K)
+    sigma = np.eye(K - 1) * 2.0 + 0.3
+    siginv, ent = c_oracle.prologue(sigma)
+    mu = rng.normal(0, 0.3, size=(D, K - 1))
+    eta0 = rng.normal(0, 0.3, size=(D, K - 1))
+    ref = c_oracle.estep(ptr, ids, cnt, beta, mu, siginv, ent, eta0, nthreads=4)
+    ctx = lib.Context(K, V, 1)
+    ctx.set_corpus(ptr, ids, cnt)
+    o = ctx.estep_host(beta, mu, siginv, ent, eta0)
+    ctx.close()
+    assert abs(o["bound"] - ref["bound"]) <= 1e-9 * abs(ref["bound"])
+    d = np.abs(o["eta"] - ref["eta"]).max(axis=1)
+    assert (d > 1e-6).mean() <= 0.002, (d > 1e-6).sum()
+    assert (o["status"] == ref["status"]).mean() >= 0.998
+    np.testing.assert_array_equal(o["repair"], ref["repair"])
+    np.testing.assert_allclose(o["sigma_ss"], ref["sigma_ss"], rtol=1e-6, atol=1e-6)
+    np.testing.assert_allclose(o["beta_ss"], ref["beta_ss"], rtol=0, atol=1e-5)
+
+
+def test_edge_cases_empty_ragged_long(lib):
+    """empty document, single-word documents, a 300-word and a 700-word document (multi-pass tiles)"""
+    K, V = 10, 1500
+    rng = np.random.default_rng(0)
+    lens = [0, 1, 1, 2, 33, 64, 65, 128, 129, 160, 161, 300, 700, 5, 0]
+    ptr, ids, cnt = [0], [], []
+    for n in lens:
+        w = np.sort(rng.choice(V, size=n, replace=False))
+        ids += list(w)
+        cnt += list(rng.integers(1, 6, size=n))
+        ptr.append(len(ids))
+    ptr, ids, cnt = np.array(ptr), np.array(ids, np.int32), np.array(cnt, np.float64)
+    beta = rng.dirichlet(np.full(V, 0.1), K).astype(np.float32).astype(np.float64) + 0.0
+    D = len(lens)
+    siginv, ent = c_oracle.prologue(np.eye(K - 1) * 5.0)
+    mu = np.zeros((D, K - 1))
+    eta0 = rng.normal(0, 0.1, size=(D, K - 1))
+    ref = c_oracle.estep(ptr, ids, cnt, beta, mu, siginv, ent, eta0)
+    ctx = lib.Context(K, V, 1)
+    ctx.set_corpus(ptr, ids, cnt)
+    o = ctx.estep_host(beta, mu, siginv, ent, eta0)
+    ctx.close()
+    np.testing.assert_allclose(o["eta"], ref["eta"], atol=1e-6)
+    np.testing.assert_allclose(o["doc_bound"], ref["doc_bound"], rtol=1e-8, atol=1e-7)
+    np.testing.assert_array_equal(o["status"], ref["status"])
+    np.testing.assert_allclose(o["beta_ss"], ref["beta_ss"], atol=1e-7)
+
+
+def test_error_behaviour(lib):
+    with pytest.raises(lib.StmError) as e:
+        lib.Context(1, 10, 1)
+    assert e.value.code == lib.STM_ERR_INVALID
+    with pytest.raises(lib.StmError) as e:
+        lib.Context(200, 10, 1)
+    assert e.value.code == lib.STM_ERR_UNSUPPORTED
+    ctx = lib.Context(4, 10, 1)
+    with pytest.raises(lib.StmError) as e:  # E-step before a corpus
+        ctx.D = 1
+        ctx.estep_host(np.full((4, 10), 0.1), np.zeros((1, 3)), np.eye(3), 0.0, np.zeros((1, 3)))
+    assert e.value.code == lib.STM_ERR_NO_CORPUS
+    with pytest.raises(lib.StmError) as e:  # word id out of range
+        ctx.set_corpus(np.array([0, 1]), np.array([10], np.int32), np.array([1.0]))
+    assert e.value.code == lib.STM_ERR_INVALID
+    ctx.set_corpus(np.array([0, 2]), np.array([1, 3], np.int32), np.array([1.0, 2.0]))
+    full = np.eye(3) + 0.1
+    with pytest.raises(lib.StmError) as e:  # the reference's siginv is diagonal (stm.py:501)
+        ctx.estep_host(np.full((4, 10), 0.1), np.zeros((1, 3)), full, 0.0, np.zeros((1, 3)))
+    assert e.value.code == lib.STM_ERR_UNSUPPORTED
+    ctx.close()
+
+
+# ---------------------------------------------------------------------------------------------------
+# the STM front: M-step parity, EM traces
+# ---------------------------------------------------------------------------------------------------
+
+def _front(g, K, model_type="STM", iters=100, thr=1e-5, **kw):
+    from strutopy_b200 import STM
+    V = int(g["V"])
+    return STM((g["doc_ptr"], g["word_id"], g["count"]), range(V), kw.pop("content", False), K, g["X"],
+               kw.pop("interactions", False), iters, 0, thr, init_type="random", model_type=model_type, **kw)
+
+
+@pytest.mark.parametrize("name,pfx", [("kat_small.npz", "it0_"), ("estep_K5.npz", "it2_"),
+                                      ("estep_K20.npz", "it0_"), ("estep_K50.npz", "it1_")])
+def test_mstep_vs_reference_fixture(name, pfx):
+    g = load_golden(name)
+    K = int(g["K"])
+    m = _front(g, K)
+    m.eta = g[pfx + "eta"]
+    m.M_step(g[pfx + "beta_ss"], g[pfx + "sigma_ss"])
+    np.testing.assert_allclose(m.gamma, g[pfx + "m_gamma"], rtol=1e-8, atol=1e-9)
+    np.testing.assert_allclose(m.mu, g[pfx + "m_mu"], rtol=1e-8, atol=1e-9)
+    np.testing.assert_allclose(m.sigma, g[pfx + "m_sigma"], rtol=1e-8, atol=1e-10)
+    if pfx + "m_beta" in g:
+        np.testing.assert_allclose(m.beta, g[pfx + "m_beta"], rtol=2e-7, atol=1e-12)  # fp32 storage
+    else:
+        np.testing.assert_allclose(m.beta, stm_numpy.update_beta(g[pfx + "beta_ss"]), rtol=2e-7, atol=1e-12)
+
+
+def test_front_estep_state_injection_matches_fixture():
+    g = load_golden("estep_K20.npz")
+    pfx = "it1_"
+    m = _front(g, int(g["K"]))
+    m.beta, m.mu, m.sigma, m.eta = g[pfx + "beta"], g[pfx + "mu"], g[pfx + "sigma"], g[pfx + "eta0"]
+    bss, sss = m.E_step()
+    assert abs(m.bound - g[pfx + "bound"]) <= 1e-9 * abs(g[pfx + "bound"])
+    np.testing.assert_allclose(m.eta, g[pfx + "eta"], atol=1e-6)
+    np.testing.assert_allclose(m.theta, g[pfx + "theta"], atol=1e-6)
+    np.testing.assert_allclose(bss, g[pfx + "beta_ss"], atol=1e-6)
+    np.testing.assert_allclose(sss, g[pfx + "sigma_ss"], rtol=1e-7, atol=1e-7)
+    np.testing.assert_allclose(m.theta.sum(axis=1), 1.0, atol=1e-12)
+
+
+def test_content_front_mstep_keeps_reference_normalisation():
+    g = load_golden("estep_content.npz")
+    K, A = int(g["K"]), int(g["A"])
+    m = _front(g, K, content=True, interactions=True, A=A, beta_index=g["aspect"])
+    pfx = "it0_"
+    m.beta, m.mu, m.sigma, m.eta = g[pfx + "beta"], g[pfx + "mu"], g[pfx + "sigma"], g[pfx + "eta0"]
+    bss, sss = m.E_step()
+    np.testing.assert_allclose(bss, g[pfx + "beta_ss"], atol=1e-6)
+    m.M_step(bss, sss)
+    np.testing.assert_allclose(m.beta, g[pfx + "m_beta"], rtol=1e-6, atol=1e-9)  # normalised over topics (stm.py:741)
+    np.testing.assert_allclose(m.sigma, g[pfx + "m_sigma"], rtol=1e-7, atol=1e-9)
+
+
+def test_em_trace_config1_vs_live_reference():
+    """BASELINE.json configs[0] (D=200 V=500 K=5, 1 covariate): full EM to convergence."""
+    g = load_golden("em_c1.npz")
+    m = _front(g, int(g["K"]))
+    m.beta = g["beta0"]
+    m.expectation_maximization(saving=False)
+    ref = g["bounds"]
+    got = np.array(m.last_bounds)
+    n = min(len(ref), len(got))
+    assert abs(len(ref) - len(got)) <= 1, (len(ref), len(got))
+    rel = np.abs((got[:n] - ref[:n]) / ref[:n])
+    assert rel[:3].max() < 1e-6, rel
+    assert rel.max() < 1e-4, rel  # north-star tolerance
+    if len(ref) == len(got):
+        np.testing.assert_allclose(m.theta, g["final_theta"], atol=2e-2)
+        np.testing.assert_allclose(m.beta, g["final_beta"], atol=1e-3)
+        np.testing.assert_allclose(m.theta.sum(axis=1), 1.0, atol=1e-9)
+        np.testing.assert_allclose(m.beta.sum(axis=1), 1.0, atol=1e-5)
+
+
+def test_em_trace_toy_ctm_vs_live_reference():
+    """the reference's own integration test pipeline (tests/test_integration.py): K=3, CTM, 2 iterations"""
+    g = load_golden("em_toy_ctm.npz")
+    m = _front(g, int(g["K"]), model_type="CTM", iters=2)
+    m.beta = g["beta0"]
+    m.expectation_maximization(saving=False)
+    np.testing.assert_allclose(m.last_bounds, g["bounds"], rtol=1e-6)
+    assert m.beta.shape == g["final_beta"].shape and m.theta.shape == g["final_theta"].shape
+    np.testing.assert_allclose(m.theta, g["final_theta"], atol=1e-4)
+    np.testing.assert_allclose(m.sigma, g["final_sigma"], atol=1e-5)
+    np.testing.assert_allclose(np.mean(m.theta.sum(axis=1)), 1.0, atol=1e-4)
+    np.testing.assert_allclose(np.mean(m.beta.sum(axis=1)), 1.0, atol=1e-4)
+
+
+def test_random_init_matches_reference_rng():
+    g = load_golden("em_c1.npz")
+    m = _front(g, int(g["K"]))
+    np.testing.assert_allclose(m.beta, g["beta0"], rtol=2e-7, atol=1e-30)  # seed 123456 gamma(0.1,1), fp32 storage
+    assert m.sigma[0, 0] == 20.0 and m.sigma[0, 1] == 0.0
+    assert not m.eta.any() and not m.mu.any()
+
+
+def test_save_model_format(tmp_path):
+    g = load_golden("estep_K5.npz")
+    m = _front(g, int(g["K"]), iters=2)
+    m.expectation_maximization(saving=True, output_dir=str(tmp_path / "out"))
+    import pickle
+    for f in ("beta_hat", "theta_hat", "sigma_hat", "eta_hat", "mu_hat", "X", "gamma_hat"):
+        assert (tmp_path / "out" / f"{f}.npy").exists()
+    assert np.load(tmp_path / "out" / "gamma_hat.npy").shape == (int(g["K"]) - 1, 1)
+    with open(tmp_path / "out" / "lower_bound.pickle", "rb") as fh:
+        assert len(pickle.load(fh)) == 2
+
+
+# ---------------------------------------------------------------------------------------------------
+# BASELINE.json full size: invariants + sampled parity
+# ---------------------------------------------------------------------------------------------------
+
+def test_full_size_invariants_and_sampled_parity(lib):
+    """D=100k, V=10k, K=50 (configs[2]): checksum of checksums (sum of phi == number of tokens),
+    simplex rows, symmetric PD sigma_ss, bitwise-reproducible eta, and parity with the C oracle on a
+    2000-document sample of the same state."""
+    import bench
+    D, V, K = 100000, 10000, 50
+    ptr, ids, cnt, X = bench.make_corpus(D, V, K)
+    beta = bench.random_beta(K, V).astype(np.float32).astype(np.float64)
+    siginv, ent = c_oracle.prologue(np.eye(K - 1) * 20.0)
+    mu = np.zeros((D, K - 1))
+    eta0 = np.zeros((D, K - 1))
+    ctx = lib.Context(K, V, 1)
+    ctx.set_corpus(ptr, ids, cnt)
+    o = ctx.estep_host(beta, mu, siginv, ent, eta0)
+    o2 = ctx.estep_host(beta, mu, siginv, ent, eta0)
+    ctx.close()
+    assert np.isfinite(o["bound"])
+    np.testing.assert_array_equal(o["eta"], o2["eta"])              # per-document path is deterministic
+    assert abs(o["bound"] - o2["bound"]) <= 1e-12 * abs(o["bound"])
+    np.testing.assert_allclose(o["theta"].sum(axis=1), 1.0, atol=1e-12)
+    tokens = float(cnt.astype(np.float64).sum())
+    assert abs(o["beta_ss"].sum() - tokens) <= 1e-9 * tokens         # sum_k phi_kv = c_v for every word
+    wc = np.bincount(ids, weights=cnt.astype(np.float64), minlength=V)
+    np.testing.assert_allclose(o["beta_ss"].sum(axis=0), wc, rtol=1e-9, atol=1e-9)
+    np.testing.assert_allclose(o["sigma_ss"], o["sigma_ss"].T, rtol=0, atol=0)
+    assert np.linalg.eigvalsh(o["sigma_ss"]).min() > 0
+    assert np.isin(o["status"], (0, 1, 2)).all()
+    # sampled parity at full size
+    sel = np.sort(np.random.default_rng(1).choice(D, size=2000, replace=False))
+    p, i, w = bench.slice_csr(ptr, ids, cnt, sel)
+    ref = c_oracle.estep(p, i, w, beta, mu[sel], siginv, ent, eta0[sel], nthreads=4)
+    d = np.abs(o["eta"][sel] - ref["eta"]).max(axis=1)
+    assert (d > 1e-6).mean() <= 0.002
+    np.testing.assert_allclose(o["doc_bound"][sel], ref["doc_bound"], rtol=1e-7, atol=1e-6)
+    assert (o["repair"][sel] == ref["repair"]).all()
