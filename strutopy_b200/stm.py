@@ -222,7 +222,7 @@ class STM:
             v = np.ascontiguousarray(np.broadcast_to(value, (self.N_local, cols)))
         else:
             v = np.ascontiguousarray(np.broadcast_to(value, (self.N, cols)))[self._lo:self._hi]
-        self._d[name].copy_(self._torch.from_numpy(np.ascontiguousarray(v)))
+        self._d[name].copy_(self._torch.from_numpy(np.array(v, dtype=np.float64, order="C", copy=True)))
         self._invalidate(name)
 
     eta = property(lambda s: s._get_rows("eta"), lambda s, v: s._set_rows("eta", v, s.K - 1))
@@ -366,7 +366,7 @@ class STM:
         if self._dist is not None:
             o4 = self._off[4]
             self._dist.all_reduce(stats[o4:])
-            stats[self._off[3]] = float(self.N)
+        stats[self._off[3]] = float(self.N)
         self._mstep_device()
         torch.cuda.current_stream(self._dev).synchronize()
         logger.info(f"Completed M-Step in {np.round(time.time() - start, 3)} seconds. \n")
