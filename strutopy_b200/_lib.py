@@ -6,7 +6,8 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libstm_b200.so")
+# STM_B200_LIB overrides the library path (development A/B builds only)
+LIB_PATH = os.environ.get("STM_B200_LIB") or os.path.join(_HERE, "libstm_b200.so")
 
 STM_OK = 0
 STM_ERR_INVALID, STM_ERR_CUDA, STM_ERR_NOT_PD, STM_ERR_UNSUPPORTED, STM_ERR_NO_CORPUS = -1, -2, -3, -4, -5

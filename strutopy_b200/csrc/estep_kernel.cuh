@@ -23,6 +23,29 @@
 #include <stdint.h>
 #include <math.h>
 
+// ---- tuning switches (A/B builds: make variant NAME=.. DEFS=..) ---------------------------------
+#ifndef STM_LOGPROD
+#define STM_LOGPROD 1      // 1: sum_v c_v log s_v as one log of a product per lane; 0: one log per word
+#endif
+#ifndef STM_Q_UNROLL
+#define STM_Q_UNROLL 1     // unroll factor of the contraction's k-group loop; 0 = compiler default
+#endif
+#ifndef STM_LOG_NOINLINE
+#define STM_LOG_NOINLINE 1 // keep log()/exp() slow paths out of line (I-cache footprint)
+#endif
+#define STM_PRAGMA2_(x) _Pragma(#x)
+#define STM_PRAGMA_(x) STM_PRAGMA2_(x)
+#if STM_Q_UNROLL > 0
+#define STM_UNROLL_Q STM_PRAGMA_(unroll STM_Q_UNROLL)
+#else
+#define STM_UNROLL_Q
+#endif
+#if STM_LOG_NOINLINE
+#define STM_NOINLINE __noinline__
+#else
+#define STM_NOINLINE __forceinline__
+#endif
+
 namespace stm {
 
 struct EstepParams {
@@ -66,13 +89,27 @@ __device__ __forceinline__ double warp_sum(double v) {
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(STM_FULL, v, o);
     return v;
 }
+// N independent sums in one butterfly: the shuffles of different values pipeline, so the latency is
+// that of ONE reduction
+template <int N>
+__device__ __forceinline__ void warp_sum_n(double (&v)[N]) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        double t[N];
+#pragma unroll
+        for (int i = 0; i < N; ++i) t[i] = __shfl_xor_sync(STM_FULL, v[i], o);
+#pragma unroll
+        for (int i = 0; i < N; ++i) v[i] += t[i];
+    }
+}
 __device__ __forceinline__ double nanmax(double a, double b) {
     return (isnan(a) || isnan(b)) ? nan("") : fmax(a, b);
 }
 __device__ __forceinline__ double warp_max(double v) {
+    const bool has_nan = __any_sync(STM_FULL, isnan(v));  // np.max propagates NaN
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v = nanmax(v, __shfl_xor_sync(STM_FULL, v, o));
-    return v;
+    for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(STM_FULL, v, o));
+    return has_nan ? nan("") : v;
 }
 
 // Python / NumPy comparison semantics used by SciPy's line searches (see oracle/stm_oracle.c)
@@ -94,74 +131,72 @@ __device__ __forceinline__ double np_sign(double x) {
     return (x > 0.0) ? 1.0 : ((x < 0.0) ? -1.0 : 0.0);
 }
 
-// MINPACK-2 dcstep — scipy/optimize/_dcsrch.py:502-728
+// MINPACK-2 dcstep — scipy/optimize/_dcsrch.py:502-728.  The four cases share ONE copy of the cubic
+// interpolation arithmetic (theta, s, gamma, r): each case performs exactly the operations of the
+// SciPy source in the same order, only the operands are selected first (instruction footprint).
 static __device__ __noinline__ void dcstep(double& stx, double& fx, double& dx, double& sty, double& fy,
                                     double& dy, double& stp, double fp, double dp, int& brackt,
                                     double stpmin, double stpmax) {
     const double sgnd = np_sign(dp) * np_sign(dx);
-    double theta, s, gamma, p, q, r, stpc, stpq, stpf;
-    if (fp > fx) {
-        theta = 3.0 * (fx - fp) / (stp - stx) + dx + dp;
-        s = py_max3(fabs(theta), fabs(dx), fabs(dp));
-        gamma = s * sqrt((theta / s) * (theta / s) - (dx / s) * (dp / s));
-        if (stp < stx) gamma = -gamma;
-        p = (gamma - dx) + theta;
-        q = ((gamma - dx) + gamma) + dp;
-        r = p / q;
-        stpc = stx + r * (stp - stx);
-        stpq = stx + ((dx / ((fx - fp) / (stp - stx) + dx)) / 2.0) * (stp - stx);
-        if (fabs(stpc - stx) <= fabs(stpq - stx)) stpf = stpc;
-        else stpf = stpc + (stpq - stpc) / 2.0;
-        brackt = 1;
-    } else if (sgnd < 0.0) {
-        theta = 3.0 * (fx - fp) / (stp - stx) + dx + dp;
-        s = py_max3(fabs(theta), fabs(dx), fabs(dp));
-        gamma = s * sqrt((theta / s) * (theta / s) - (dx / s) * (dp / s));
-        if (stp > stx) gamma = -gamma;
-        p = (gamma - dp) + theta;
-        q = ((gamma - dp) + gamma) + dx;
-        r = p / q;
-        stpc = stp + r * (stx - stp);
-        stpq = stp + (dp / (dp - dx)) * (stx - stp);
-        if (fabs(stpc - stp) > fabs(stpq - stp)) stpf = stpc;
-        else stpf = stpq;
-        brackt = 1;
-    } else if (fabs(dp) < fabs(dx)) {
-        theta = 3.0 * (fx - fp) / (stp - stx) + dx + dp;
-        s = py_max3(fabs(theta), fabs(dx), fabs(dp));
-        gamma = s * sqrt(py_max2(0.0, (theta / s) * (theta / s) - (dx / s) * (dp / s)));
-        if (stp > stx) gamma = -gamma;
-        p = (gamma - dp) + theta;
-        q = (gamma + (dx - dp)) + gamma;
-        r = p / q;
-        if (r < 0.0 && gamma != 0.0) stpc = stp + r * (stx - stp);
-        else if (stp > stx) stpc = stpmax;
-        else stpc = stpmin;
-        stpq = stp + (dp / (dp - dx)) * (stx - stp);
-        if (brackt) {
-            if (fabs(stpc - stp) < fabs(stpq - stp)) stpf = stpc;
-            else stpf = stpq;
-            if (stp > stx) stpf = py_min2(stp + 0.66 * (sty - stp), stpf);
-            else stpf = py_max2(stp + 0.66 * (sty - stp), stpf);
+    int cs;  // 1..4: the four Moré–Thuente cases; 0: case 4 without a bracket (no interpolation)
+    if (fp > fx) cs = 1;
+    else if (sgnd < 0.0) cs = 2;
+    else if (fabs(dp) < fabs(dx)) cs = 3;
+    else cs = brackt ? 4 : 0;
+    double stpf;
+    if (cs != 0) {
+        // theta = 3 (f1 - f2) / (s2 - s1) + d1 + dp
+        const double f1 = (cs == 4) ? fp : fx, f2 = (cs == 4) ? fy : fp;
+        const double s2 = (cs == 4) ? sty : stp, s1 = (cs == 4) ? stp : stx;
+        const double d1 = (cs == 4) ? dy : dx;
+        const double theta = 3.0 * (f1 - f2) / (s2 - s1) + d1 + dp;
+        const double s = py_max3(fabs(theta), fabs(d1), fabs(dp));
+        double arg = (theta / s) * (theta / s) - (d1 / s) * (dp / s);
+        if (cs == 3) arg = py_max2(0.0, arg);
+        double gamma = s * sqrt(arg);
+        const bool flip = (cs == 1) ? (stp < stx) : ((cs == 4) ? (stp > sty) : (stp > stx));
+        if (flip) gamma = -gamma;
+        double p, q;
+        if (cs == 1) { p = (gamma - dx) + theta; q = ((gamma - dx) + gamma) + dp; }
+        else if (cs == 2) { p = (gamma - dp) + theta; q = ((gamma - dp) + gamma) + dx; }
+        else if (cs == 3) { p = (gamma - dp) + theta; q = (gamma + (dx - dp)) + gamma; }
+        else { p = (gamma - dp) + theta; q = ((gamma - dp) + gamma) + dy; }
+        const double r = p / q;
+        if (cs == 1) {
+            const double stpc = stx + r * (stp - stx);
+            const double stpq = stx + ((dx / ((fx - fp) / (stp - stx) + dx)) / 2.0) * (stp - stx);
+            if (fabs(stpc - stx) <= fabs(stpq - stx)) stpf = stpc;
+            else stpf = stpc + (stpq - stpc) / 2.0;
+            brackt = 1;
+        } else if (cs == 4) {
+            stpf = stp + r * (sty - stp);
         } else {
-            if (fabs(stpc - stp) > fabs(stpq - stp)) stpf = stpc;
-            else stpf = stpq;
-            stpf = np_clip(stpf, stpmin, stpmax);
+            const double stpq = stp + (dp / (dp - dx)) * (stx - stp);
+            if (cs == 2) {
+                const double stpc = stp + r * (stx - stp);
+                if (fabs(stpc - stp) > fabs(stpq - stp)) stpf = stpc;
+                else stpf = stpq;
+                brackt = 1;
+            } else {
+                double stpc;
+                if (r < 0.0 && gamma != 0.0) stpc = stp + r * (stx - stp);
+                else if (stp > stx) stpc = stpmax;
+                else stpc = stpmin;
+                if (brackt) {
+                    if (fabs(stpc - stp) < fabs(stpq - stp)) stpf = stpc;
+                    else stpf = stpq;
+                    if (stp > stx) stpf = py_min2(stp + 0.66 * (sty - stp), stpf);
+                    else stpf = py_max2(stp + 0.66 * (sty - stp), stpf);
+                } else {
+                    if (fabs(stpc - stp) > fabs(stpq - stp)) stpf = stpc;
+                    else stpf = stpq;
+                    stpf = np_clip(stpf, stpmin, stpmax);
+                }
+            }
         }
-    } else {
-        if (brackt) {
-            theta = 3.0 * (fp - fy) / (sty - stp) + dy + dp;
-            s = py_max3(fabs(theta), fabs(dy), fabs(dp));
-            gamma = s * sqrt((theta / s) * (theta / s) - (dy / s) * (dp / s));
-            if (stp > sty) gamma = -gamma;
-            p = (gamma - dp) + theta;
-            q = ((gamma - dp) + gamma) + dy;
-            r = p / q;
-            stpc = stp + r * (sty - stp);
-            stpf = stpc;
-        } else if (stp > stx) stpf = stpmax;
-        else stpf = stpmin;
-    }
+    } else if (stp > stx) stpf = stpmax;
+    else stpf = stpmin;
+
     if (fp > fx) {
         sty = stp; fy = fp; dy = dp;
     } else {
@@ -197,6 +232,49 @@ static __device__ __noinline__ double quadmin(double a, double fa, double fpa, d
     const double xmin = a - C / (2.0 * B);
     if (!isfinite(xmin)) return nan("");
     return xmin;
+}
+
+// log() kept out of line: it is only needed once per lane per evaluation (see logprod_*), so one
+// shared copy keeps the hot loop's instruction footprint small (the kernel is I-cache sensitive).
+static __device__ STM_NOINLINE double log_noinline(double x) { return log(x); }
+static __device__ STM_NOINLINE double exp_noinline(double x) { return exp(x); }
+
+// sum_v c_v log(s_v) accumulated as a PRODUCT: s = m2 * 2^e (m2 in [1,2)), prod *= m2^c, esum += c*e.
+// One log per lane per evaluation instead of one per word.  Falls back to c*log(s) for
+// non-integer / large counts and for zero, subnormal, negative or non-finite s.
+struct LogProd {
+    double prod;   // running mantissa product, kept in [1, 2^64)
+    double esum;   // running exponent sum (exact small integers)
+    double extra;  // fallback terms c*log(s)
+};
+__device__ __forceinline__ void logprod_init(LogProd& a) { a.prod = 1.0; a.esum = 0.0; a.extra = 0.0; }
+__device__ __forceinline__ void logprod_renorm(LogProd& a) {
+    const int hi = __double2hiint(a.prod);
+    const int e = ((hi >> 20) & 0x7ff) - 1023;
+    a.esum += (double)e;
+    a.prod = __hiloint2double((hi & 0x800fffff) | 0x3ff00000, __double2loint(a.prod));
+}
+__device__ __forceinline__ void logprod_add(LogProd& a, double s, float cf) {
+    const int hi = __double2hiint(s);
+    const int be = (hi >> 20) & 0x7ff;           // biased exponent; sign bit excluded below
+    const int ci = (int)cf;
+    const bool fast = (hi > 0) && (be != 0) && (be != 0x7ff) && ((float)ci == cf) && (ci >= 1) && (ci <= 8);
+    if (fast) {
+        const double m2 = __hiloint2double((hi & 0x000fffff) | 0x3ff00000, __double2loint(s));
+        // m2^ci for ci in 1..8 without a loop: m2^(b0) * (m2^2)^(b1) * (m2^4)^(b2) * (m2^8)^(b3)
+        const double q2 = m2 * m2, q4 = q2 * q2;
+        double pw = (ci & 1) ? m2 : 1.0;
+        if (ci & 2) pw *= q2;
+        if (ci & 4) pw *= q4;
+        if (ci & 8) pw *= q4 * q4;
+        a.prod *= pw;
+        a.esum += (double)(ci * (be - 1023));
+    } else {
+        a.extra += (double)cf * log_noinline(s);
+    }
+}
+__device__ __forceinline__ double logprod_value(const LogProd& a) {
+    return a.esum * 0.6931471805599453 + log_noinline(a.prod) + a.extra;
 }
 
 // ---- TMA bulk copy + mbarrier (PTX) -----------------------------------------------------------
@@ -236,6 +314,88 @@ __device__ __forceinline__ void red_add_f64(double* addr, double v) {
     asm volatile("red.global.add.f64 [%0], %1;" ::"l"(addr), "d"(v) : "memory");
 }
 
+// ---- dense (K-1)x(K-1) helpers on a shared-memory matrix, one warp, out of line -------------------
+// Storage convention: Hm is [K1][HS] (HS odd).  The UPPER triangle keeps the original symmetric
+// matrix; the strict LOWER triangle receives the Cholesky factor; its diagonal goes to Ld.
+
+// left-looking Cholesky, lane <-> row, inner products as 4 interleaved partial sums; the pivot
+// H_jj - sum_k<j L_jk^2 is kept as a running diagonal Dw (same subtraction order as a sequential loop).
+static __device__ __noinline__ int chol_factor(double* Hm, double* Dw, const double* Dg, double* Ld,
+                                               int K1, int HS, int lane) {
+    for (int k = lane; k < K1; k += 32) Dw[k] = Dg[k];
+    __syncwarp();
+    for (int j = 0; j < K1; ++j) {
+        const double djj = Dw[j];
+        if (!(djj > 0.0)) return 0;
+        const double ljj = sqrt(djj);
+        const double inv = 1.0 / ljj;
+        if (lane == 0) Ld[j] = ljj;
+        const double* Lj = Hm + (size_t)j * HS;
+        for (int i = j + 1 + lane; i < K1; i += 32) {
+            const double* Li_ = Hm + (size_t)i * HS;
+            double t0 = 0.0, t1 = 0.0, t2 = 0.0, t3 = 0.0;
+            int k = 0;
+            for (; k + 4 <= j; k += 4) {
+                t0 = fma(Li_[k], Lj[k], t0);
+                t1 = fma(Li_[k + 1], Lj[k + 1], t1);
+                t2 = fma(Li_[k + 2], Lj[k + 2], t2);
+                t3 = fma(Li_[k + 3], Lj[k + 3], t3);
+            }
+            for (; k < j; ++k) t0 = fma(Li_[k], Lj[k], t0);
+            const double lij = (Lj[i] - ((t0 + t1) + (t2 + t3))) * inv;  // upper triangle holds H_ij
+            Hm[(size_t)i * HS + j] = lij;
+            Dw[i] = Dw[i] - lij * lij;
+        }
+        __syncwarp();
+    }
+    return 1;
+}
+
+// nu = H^-1 = L^-T L^-1 (stm.py:1052-1066), accumulated into sigma_ss (stm.py:582).
+// Li = L^-1 (lower) is stored transposed in the UPPER triangle: Hm[j][i] = Li[i][j], i >= j.
+//   row i for all columns j < i in parallel (lane <-> j):
+//   Li[i][j] = -(sum_{k=j}^{i-1} L[i][k] Li[k][j]) / L[i][i],   Li[i][i] = 1 / L[i][i]
+static __device__ __noinline__ void inverse_and_nu(double* Hm, const double* Ld, double* sig_acc, int K1,
+                                                   int HS, int lane) {
+    for (int i = 0; i < K1; ++i) {
+        const double inv = 1.0 / Ld[i];
+        const double* Li_ = Hm + (size_t)i * HS;
+        if (lane == 0) Hm[(size_t)i * HS + i] = inv;
+        for (int j = lane; j < i; j += 32) {
+            const double* Uj = Hm + (size_t)j * HS;
+            double t0 = 0.0, t1 = 0.0, t2 = 0.0, t3 = 0.0;
+            int k = j;
+            for (; k + 4 <= i; k += 4) {
+                t0 = fma(Li_[k], Uj[k], t0);
+                t1 = fma(Li_[k + 1], Uj[k + 1], t1);
+                t2 = fma(Li_[k + 2], Uj[k + 2], t2);
+                t3 = fma(Li_[k + 3], Uj[k + 3], t3);
+            }
+            for (; k < i; ++k) t0 = fma(Li_[k], Uj[k], t0);
+            Hm[(size_t)j * HS + i] = -((t0 + t1) + (t2 + t3)) * inv;
+        }
+        __syncwarp();
+    }
+    // nu_ij = sum_{k>=i} Li[k][i] Li[k][j]  (i >= j): row i of the upper storage dotted with row j
+    int i = 0;
+    for (int idx = lane; idx < K1 * (K1 + 1) / 2; idx += 32) {
+        while ((i + 1) * (i + 2) / 2 <= idx) i++;
+        const int j = idx - i * (i + 1) / 2;
+        const double* Ui = Hm + (size_t)i * HS;
+        const double* Uj = Hm + (size_t)j * HS;
+        double t0 = 0.0, t1 = 0.0, t2 = 0.0, t3 = 0.0;
+        int k = i;
+        for (; k + 4 <= K1; k += 4) {
+            t0 = fma(Ui[k], Uj[k], t0);
+            t1 = fma(Ui[k + 1], Uj[k + 1], t1);
+            t2 = fma(Ui[k + 2], Uj[k + 2], t2);
+            t3 = fma(Ui[k + 3], Uj[k + 3], t3);
+        }
+        for (; k < K1; ++k) t0 = fma(Ui[k], Uj[k], t0);
+        red_add_f64(sig_acc + (size_t)i * K1 + j, (t0 + t1) + (t2 + t3));
+    }
+}
+
 // status / repair codes mirror oracle/stm_oracle.h
 enum { LS_INIT = 0, LS_W1 = 1, LS_W2 = 2, LS_ZOOM = 3 };
 
@@ -258,7 +418,8 @@ __global__ void __launch_bounds__(256, 1) estep_kernel(const EstepParams P) {
     float* tile = reinterpret_cast<float*>(base);
     double* Hm = reinterpret_cast<double*>(base);  // aliases the tile once it is dead
     double* wv = reinterpret_cast<double*>(base + tile_bytes);            // [n_cap] per-word fp64
-    double* vec = wv + P.n_cap;                                           // [4][KVS]
+    double* wv2 = wv + P.n_cap;                                           // [n_cap] sqrt(c_v)
+    double* vec = wv2 + P.n_cap;                                          // [4][KVS]
     float* cw = reinterpret_cast<float*>(vec + 4 * KVS);                  // [n_cap] counts
     int* wid = reinterpret_cast<int*>(cw + P.n_cap);                      // [n_cap]
     uint64_t* mbar = reinterpret_cast<uint64_t*>(wid + P.n_cap);
@@ -393,56 +554,68 @@ __global__ void __launch_bounds__(256, 1) estep_kernel(const EstepParams P) {
                         m = nanmax(m, et[i]);
                     }
                     m = warp_max(m);
-                    double cnt_l = 0.0, s_l = 0.0, q_l = 0.0;
+                    // red[]: cnt, ssum, quad, data, (S d - a).p, ex.p  — reduced together after the contraction
+                    double red[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
 #pragma unroll
                     for (int i = 0; i < KPL; ++i) {
                         const int k = lane + 32 * i;
-                        ex[i] = exp(et[i] - m);
-                        if (k < K) { if (et[i] == m) cnt_l += 1.0; else s_l += ex[i]; }
+                        ex[i] = exp_noinline(et[i] - m);
+                        if (k < K) { if (et[i] == m) red[0] += 1.0; else red[1] += ex[i]; }
                         v0[k] = (k < K) ? ex[i] : 0.0;
                         const double dk = xt[i] - mu[i];
-                        q_l += (Sd[i] * dk) * dk;
+                        const double sdk = Sd[i] * dk;
+                        red[2] += sdk * dk;
+                        if (k < K1) { red[4] += (sdk - a[i]) * p[i]; red[5] += ex[i] * p[i]; }
                     }
                     __syncwarp();
-                    const double cnt = warp_sum(cnt_l);
-                    double ssum = warp_sum(s_l);
-                    const double se_all = ssum + cnt;
-                    if (ssum != 0.0) ssum = ssum / cnt;
-                    // scipy.special.logsumexp (scipy/special/_logsumexp.py:201-247)
-                    const double lse = log1p(ssum) + log(cnt) + m;
-                    const double quad = 0.5 * warp_sum(q_l);
 
                     // data term: sum_v c_v (m + log(sum_k e_k beta_kv))           stm.py:938-941
-                    double part = 0.0;
+                    LogProd lp;
+                    logprod_init(lp);
                     for (int w0 = 0; w0 < n; w0 += 32 * J) {
-                        double acc[J];
+                        double acc[J][2];
                         const float4* rows[J];
 #pragma unroll
                         for (int j = 0; j < J; ++j) {
-                            acc[j] = 0.0;
+                            acc[j][0] = 0.0; acc[j][1] = 0.0;
                             int v = w0 + lane + 32 * j;
                             if (v >= n) v = n - 1;
                             rows[j] = reinterpret_cast<const float4*>(tile + (size_t)v * TS);
                         }
                         const double2* e2 = reinterpret_cast<const double2*>(v0);
+                        STM_UNROLL_Q
                         for (int q = 0; q < TS / 4; ++q) {
                             const double2 ea = e2[2 * q], eb = e2[2 * q + 1];
 #pragma unroll
                             for (int j = 0; j < J; ++j) {
                                 const float4 b = rows[j][q];
-                                acc[j] = fma(ea.x, (double)b.x, acc[j]);
-                                acc[j] = fma(ea.y, (double)b.y, acc[j]);
-                                acc[j] = fma(eb.x, (double)b.z, acc[j]);
-                                acc[j] = fma(eb.y, (double)b.w, acc[j]);
+                                acc[j][0] = fma(ea.x, (double)b.x, acc[j][0]);
+                                acc[j][1] = fma(ea.y, (double)b.y, acc[j][1]);
+                                acc[j][0] = fma(eb.x, (double)b.z, acc[j][0]);
+                                acc[j][1] = fma(eb.y, (double)b.w, acc[j][1]);
                             }
                         }
 #pragma unroll
                         for (int j = 0; j < J; ++j) {
                             const int v = w0 + lane + 32 * j;
-                            if (v < n) part += (double)cw[v] * (m + log(acc[j]));
+#if STM_LOGPROD
+                            if (v < n) logprod_add(lp, acc[j][0] + acc[j][1], cw[v]);
+#else
+                            if (v < n) lp.extra += (double)cw[v] * log(acc[j][0] + acc[j][1]);
+#endif
                         }
+                        logprod_renorm(lp);
                     }
-                    const double data = warp_sum(part);
+                    red[3] = logprod_value(lp);
+                    warp_sum_n<6>(red);
+                    const double cnt = red[0];
+                    double ssum = red[1];
+                    const double se_all = ssum + cnt;
+                    if (ssum != 0.0) ssum = ssum / cnt;
+                    // scipy.special.logsumexp (scipy/special/_logsumexp.py:201-247)
+                    const double lse = log_noinline(1.0 + ssum) + ((cnt == 1.0) ? 0.0 : log_noinline(cnt)) + m;
+                    const double quad = 0.5 * red[2];
+                    const double data = m * Nsum + red[3];
                     f_eval = quad - (data - Nint * lse);
 
                     // gradient stm.py:946-958 (beta NOT weighted by exp(eta): reference quirk)
@@ -453,12 +626,13 @@ __global__ void __launch_bounds__(256, 1) estep_kernel(const EstepParams P) {
                         const double dk = xt[i] - mu[i];
                         gt[i] = (k < K1) ? (Sd[i] * dk - (a[i] - scale * ex[i])) : 0.0;
                     }
-                    __syncwarp();
-                }
-                double dp_l2 = 0.0;
+                    dphi = red[4] + scale * red[5];   // = gt . p
+                } else {
+                    double dp_l2 = 0.0;
 #pragma unroll
-                for (int i = 0; i < KPL; ++i) dp_l2 += gt[i] * p[i];
-                dphi = warp_sum(dp_l2);
+                    for (int i = 0; i < KPL; ++i) dp_l2 += gt[i] * p[i];
+                    dphi = warp_sum(dp_l2);
+                }
             }
 
             // ---------------- consume the evaluation --------------------------------------------
@@ -770,25 +944,35 @@ __global__ void __launch_bounds__(256, 1) estep_kernel(const EstepParams P) {
             __syncwarp();
         }
         // colsum_v = sum_k e_k beta_kv and the log-likelihood part of the bound (stm.py:1088-1096)
-        double ll_l = 0.0;
-        for (int v = lane; v < n; v += 32) {
-            const float4* row = reinterpret_cast<const float4*>(tile + (size_t)v * TS);
+        double loglik;
+        {
+            LogProd lp;
+            logprod_init(lp);
             const double2* e2 = reinterpret_cast<const double2*>(v0);
             const double2* t2 = reinterpret_cast<const double2*>(v1);
-            double s = 0.0, t = 0.0;
-            for (int q = 0; q < TS / 4; ++q) {
-                const float4 b = row[q];
-                const double2 ea = e2[2 * q], eb = e2[2 * q + 1], ta = t2[2 * q], tb = t2[2 * q + 1];
-                s = fma(ea.x, (double)b.x, s); s = fma(ea.y, (double)b.y, s);
-                s = fma(eb.x, (double)b.z, s); s = fma(eb.y, (double)b.w, s);
-                t = fma(ta.x, (double)b.x, t); t = fma(ta.y, (double)b.y, t);
-                t = fma(tb.x, (double)b.z, t); t = fma(tb.y, (double)b.w, t);
+#pragma unroll 1
+            for (int v = lane; v < n; v += 32) {
+                const float4* row = reinterpret_cast<const float4*>(tile + (size_t)v * TS);
+                double s0 = 0.0, s1 = 0.0, t0 = 0.0, t1 = 0.0;
+#pragma unroll 1
+                for (int q = 0; q < TS / 4; ++q) {
+                    const float4 bq = row[q];
+                    const double2 ea = e2[2 * q], eb = e2[2 * q + 1], wa = t2[2 * q], wb = t2[2 * q + 1];
+                    const double b0 = (double)bq.x, b1 = (double)bq.y, b2 = (double)bq.z, b3 = (double)bq.w;
+                    s0 = fma(ea.x, b0, s0); t0 = fma(wa.x, b0, t0);
+                    s1 = fma(ea.y, b1, s1); t1 = fma(wa.y, b1, t1);
+                    s0 = fma(eb.x, b2, s0); t0 = fma(wb.x, b2, t0);
+                    s1 = fma(eb.y, b3, s1); t1 = fma(wb.y, b3, t1);
+                }
+                const float cf = cw[v];
+                logprod_add(lp, t0 + t1, cf);
+                logprod_renorm(lp);
+                const double sq = sqrt((double)cf);
+                wv[v] = sq / (s0 + s1);   // sqrt(c_v)/colsum_v
+                wv2[v] = sq;
             }
-            const double c = (double)cw[v];
-            ll_l += log(t) * c;
-            wv[v] = sqrt(c) / s;   // sqrt(c_v)/colsum_v
+            loglik = warp_sum(logprod_value(lp));
         }
-        const double loglik = warp_sum(ll_l);
         __syncwarp();
 
         // Hessian data term  sum_v b_v b_v'  with b_kv = beta_kv e_k sqrt(c_v)/colsum_v (stm.py:1000-1006),
@@ -821,7 +1005,7 @@ __global__ void __launch_bounds__(256, 1) estep_kernel(const EstepParams P) {
                 for (int v = 0; v < n; ++v) {
                     double* bv = bbuf + (v & 1) * KVS;
                     const double sc = wv[v];
-                    const double sqc = sqrt((double)cw[v]);
+                    const double sqc = wv2[v];
 #pragma unroll
                     for (int i = 0; i < KPL; ++i) {
                         const int k = lane + 32 * i;
@@ -889,27 +1073,12 @@ __global__ void __launch_bounds__(256, 1) estep_kernel(const EstepParams P) {
         int repair = 0;
         double* Ld = v2;      // diagonal of L
         double* Dg = v3;      // diagonal of H (original / repaired)
+        double* Dw = v0;      // running diagonal  H_jj - sum_k<j L_jk^2  (same order as a sequential loop)
         for (int k = lane; k < K1; k += 32) Dg[k] = Hm[(size_t)k * HS + k];
         __syncwarp();
         int upper = 0;
         for (int attempt = 0;; ++attempt) {
-            // left-looking Cholesky: lane owns rows
-            int ok = 1;
-            for (int j = 0; j < K1 && ok; ++j) {
-                // d = H_jj - sum_k<j L_jk^2
-                double s_l = 0.0;
-                for (int k = lane; k < j; k += 32) { const double l = Hm[(size_t)j * HS + k]; s_l = fma(l, l, s_l); }
-                const double djj = Dg[j] - warp_sum(s_l);
-                if (!(djj > 0.0)) { ok = 0; break; }
-                const double ljj = sqrt(djj);
-                if (lane == 0) Ld[j] = ljj;
-                for (int i = j + 1 + lane; i < K1; i += 32) {
-                    double t = Hm[(size_t)j * HS + i];  // upper triangle holds the original H_ij
-                    for (int k = 0; k < j; ++k) t = fma(-Hm[(size_t)i * HS + k], Hm[(size_t)j * HS + k], t);
-                    Hm[(size_t)i * HS + j] = t / ljj;
-                }
-                __syncwarp();
-            }
+            const int ok = chol_factor(Hm, Dw, Dg, Ld, K1, HS, lane);
             if (ok) break;
             // failed: restore the lower triangle from the upper one, then repair
             __syncwarp();
@@ -944,7 +1113,7 @@ __global__ void __launch_bounds__(256, 1) estep_kernel(const EstepParams P) {
 
         // bound (stm.py:1085-1100)
         double det_l = 0.0, q_l = 0.0;
-        for (int k = lane; k < K1; k += 32) det_l += log(Ld[k]);
+        for (int k = lane; k < K1; k += 32) det_l += log_noinline(Ld[k]);
 #pragma unroll
         for (int i = 0; i < KPL; ++i) { const double dk = x[i] - mu[i]; q_l += (Sd[i] * dk) * dk; }
         const double bound = loglik - warp_sum(det_l) - 0.5 * warp_sum(q_l) - sigmaentropy;
@@ -957,29 +1126,7 @@ __global__ void __launch_bounds__(256, 1) estep_kernel(const EstepParams P) {
 
         // nu = H^-1 = L^-T L^-1 (stm.py:1052-1066), accumulated into sigma_ss (stm.py:582)
         if (!upper) {
-            // Li = L^-1 (lower), stored transposed in the UPPER triangle: Hm[j][i] = Li[i][j], i >= j.
-            // Row i of Li for all columns j < i in parallel (lane <-> j):
-            //   Li[i][j] = -(sum_{k=j}^{i-1} L[i][k] Li[k][j]) / L[i][i],   Li[i][i] = 1 / L[i][i]
-            for (int i = 0; i < K1; ++i) {
-                const double inv = 1.0 / Ld[i];
-                for (int j = lane; j < i; j += 32) {
-                    double t = 0.0;
-                    for (int k = j; k < i; ++k) t = fma(Hm[(size_t)i * HS + k], Hm[(size_t)j * HS + k], t);
-                    Hm[(size_t)j * HS + i] = -t * inv;
-                }
-                if (lane == 0) Hm[(size_t)i * HS + i] = inv;
-                __syncwarp();
-            }
-            // nu_ij = sum_{k>=i} Li[k][i] Li[k][j]  (i >= j): row i of the upper storage dotted with row j
-            for (int idx = lane; idx < K1 * (K1 + 1) / 2; idx += 32) {
-                int i = (int)((sqrt(8.0 * idx + 1.0) - 1.0) * 0.5);
-                while ((i + 1) * (i + 2) / 2 <= idx) i++;
-                while (i * (i + 1) / 2 > idx) i--;
-                const int j = idx - i * (i + 1) / 2;
-                double t = 0.0;
-                for (int k = i; k < K1; ++k) t = fma(Hm[(size_t)i * HS + k], Hm[(size_t)j * HS + k], t);
-                red_add_f64(sig_acc + (size_t)i * K1 + j, t);
-            }
+            inverse_and_nu(Hm, Ld, sig_acc, K1, HS, lane);
         } else {
             for (int k = lane; k < K1; k += 32) {
                 const double il = 1.0 / Ld[k];

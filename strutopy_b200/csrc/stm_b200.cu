@@ -108,7 +108,7 @@ size_t smem_per_warp_bytes(int n_cap, int TS, int K1, int KPL) {
     if (hb > tile) tile = hb;
     tile = (tile + 127) & ~(size_t)127;
     const int KVS = KPL * 32 + 8;
-    size_t total = tile + (size_t)n_cap * 8 + (size_t)4 * KVS * 8 + (size_t)n_cap * 4 + (size_t)n_cap * 4 + 8;
+    size_t total = tile + (size_t)n_cap * 16 + (size_t)4 * KVS * 8 + (size_t)n_cap * 4 + (size_t)n_cap * 4 + 8;
     return (total + 127) & ~(size_t)127;
 }
 
@@ -492,8 +492,11 @@ int stm_set_corpus(stm_ctx* ctx, int64_t D, const int64_t* doc_ptr, const int32_
     for (int ci = 0; ci < ncaps; ++ci) {
         if (members[ci].empty()) continue;
         LengthClass lc;
-        lc.n_cap = caps[ci];
-        lc.J = lc.n_cap <= 64 ? 2 : (lc.n_cap <= 128 ? 4 : (lc.n_cap <= 160 ? 5 : 8));
+        lc.J = caps[ci] <= 64 ? 2 : (caps[ci] <= 128 ? 4 : (caps[ci] <= 160 ? 5 : 8));
+        // exact fit: tile capacity = longest document of the class (rounded to 4 rows), not the class bound
+        int longest = 1;
+        for (int dd : members[ci]) longest = std::max<int>(longest, (int)(doc_ptr[dd + 1] - doc_ptr[dd]));
+        lc.n_cap = std::min(caps[ci], (longest + 3) / 4 * 4);
         lc.n_docs = (int)members[ci].size();
         // longest documents first: better tail balance on the dynamic queue
         std::stable_sort(members[ci].begin(), members[ci].end(), [&](int a, int b) {

@@ -1,0 +1,56 @@
+"""A/B timing of the E-step kernel (development tool).  Usage on the GPU box:
+    STM_B200_LIB=path/to/lib.so python tools/gpu_perf.py [--iters 4] [--docs 100000]
+Prints per-EM-iteration E-step kernel time (CUDA events), mean evaluations per document, ELBO."""
+import argparse
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import bench  # noqa: E402
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--iters", type=int, default=4)
+    ap.add_argument("--docs", type=int, default=100000)
+    ap.add_argument("--K", type=int, default=50)
+    ap.add_argument("--V", type=int, default=10000)
+    ap.add_argument("--tag", default=os.environ.get("STM_B200_LIB", "default"))
+    a = ap.parse_args()
+    import torch
+    cache = f"/tmp/corpus_{a.docs}_{a.V}_{a.K}.npz"
+    if os.path.exists(cache):
+        z = np.load(cache)
+        ptr, ids, cnt, X = z["ptr"], z["ids"], z["cnt"], z["X"]
+    else:
+        ptr, ids, cnt, X = bench.make_corpus(a.docs, a.V, a.K)
+        np.savez(cache, ptr=ptr, ids=ids, cnt=cnt, X=X)
+    from strutopy_b200 import STM
+    m = STM((ptr, ids, cnt), range(a.V), False, a.K, X, False, 10 ** 9, 0, 0.0, init_type="random",
+            model_type="STM", device=0)
+    m.beta = bench.random_beta(a.K, a.V)
+    out = []
+    for it in range(a.iters):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record()
+        m._estep_device()
+        e1.record()
+        b = m._reduce_and_bound()
+        t = time.perf_counter()
+        m._mstep_device()
+        torch.cuda.synchronize()
+        tm = time.perf_counter() - t
+        d = m.doc_diagnostics()
+        out.append(f"it{it}: estep {e0.elapsed_time(e1):7.2f} ms  nfev {d['nfev'].mean():5.1f}  nit {d['nit'].mean():4.2f} "
+                   f"repair {np.mean(d['repair'] > 0):.2f}  mstep {tm*1e3:5.2f} ms  bound {b:.6f}")
+    print(f"== {a.tag}")
+    print("\n".join(out), flush=True)
+
+
+if __name__ == "__main__":
+    main()
