@@ -30,6 +30,9 @@
 #ifndef STM_Q_UNROLL
 #define STM_Q_UNROLL 1     // unroll factor of the contraction's k-group loop; 0 = compiler default
 #endif
+#ifndef STM_INT_CVT
+#define STM_INT_CVT 1      // 1: integer fp32->fp64 conversion of beta (IMAD.WIDE); 0: F2F (XU pipe)
+#endif
 #ifndef STM_LOG_NOINLINE
 #define STM_LOG_NOINLINE 1 // keep log()/exp() slow paths out of line (I-cache footprint)
 #endif
@@ -232,6 +235,20 @@ static __device__ __noinline__ double quadmin(double a, double fa, double fpa, d
     const double xmin = a - C / (2.0 * B);
     if (!isfinite(xmin)) return nan("");
     return xmin;
+}
+
+// fp32 -> fp64 of a NON-NEGATIVE beta entry with ONE integer multiply-add (IMAD.WIDE) instead of
+// F2F.F64.F32: conversions run on the XU pipe at 1/8 rate and saturated it (profiles/r01b).
+// bits64 = bits32 * 2^29 + (896 << 52): exact for every normal float; 0 and subnormals
+// (< 1.18e-38) map to [2^-127, 2^-126), i.e. an absolute error below 1.2e-38.
+__device__ __forceinline__ double beta_f2d(float f) {
+#if STM_INT_CVT
+    const unsigned long long r =
+        (unsigned long long)__float_as_uint(f) * 0x20000000ull + 0x3800000000000000ull;
+    return __longlong_as_double((long long)r);
+#else
+    return (double)f;
+#endif
 }
 
 // log() kept out of line: it is only needed once per lane per evaluation (see logprod_*), so one
@@ -494,7 +511,7 @@ __global__ void __launch_bounds__(256, 1) estep_kernel(const EstepParams P) {
             double cs = 0.0;
             for (int q = 0; q < TS / 4; ++q) {
                 const float4 b = row[q];
-                cs += (double)b.x; cs += (double)b.y; cs += (double)b.z; cs += (double)b.w;
+                cs += beta_f2d(b.x); cs += beta_f2d(b.y); cs += beta_f2d(b.z); cs += beta_f2d(b.w);
             }
             wv[v] = (double)cw[v] / cs;
         }
@@ -504,7 +521,7 @@ __global__ void __launch_bounds__(256, 1) estep_kernel(const EstepParams P) {
 #pragma unroll
             for (int i = 0; i < KPL; ++i) {
                 const int k = lane + 32 * i;
-                if (k < K) a[i] += (double)tile[(size_t)v * TS + k] * r;
+                if (k < K) a[i] += beta_f2d(tile[(size_t)v * TS + k]) * r;
             }
         }
         __syncwarp();
@@ -589,10 +606,10 @@ __global__ void __launch_bounds__(256, 1) estep_kernel(const EstepParams P) {
 #pragma unroll
                             for (int j = 0; j < J; ++j) {
                                 const float4 b = rows[j][q];
-                                acc[j][0] = fma(ea.x, (double)b.x, acc[j][0]);
-                                acc[j][1] = fma(ea.y, (double)b.y, acc[j][1]);
-                                acc[j][0] = fma(eb.x, (double)b.z, acc[j][0]);
-                                acc[j][1] = fma(eb.y, (double)b.w, acc[j][1]);
+                                acc[j][0] = fma(ea.x, beta_f2d(b.x), acc[j][0]);
+                                acc[j][1] = fma(ea.y, beta_f2d(b.y), acc[j][1]);
+                                acc[j][0] = fma(eb.x, beta_f2d(b.z), acc[j][0]);
+                                acc[j][1] = fma(eb.y, beta_f2d(b.w), acc[j][1]);
                             }
                         }
 #pragma unroll
@@ -958,7 +975,7 @@ __global__ void __launch_bounds__(256, 1) estep_kernel(const EstepParams P) {
                 for (int q = 0; q < TS / 4; ++q) {
                     const float4 bq = row[q];
                     const double2 ea = e2[2 * q], eb = e2[2 * q + 1], wa = t2[2 * q], wb = t2[2 * q + 1];
-                    const double b0 = (double)bq.x, b1 = (double)bq.y, b2 = (double)bq.z, b3 = (double)bq.w;
+                    const double b0 = beta_f2d(bq.x), b1 = beta_f2d(bq.y), b2 = beta_f2d(bq.z), b3 = beta_f2d(bq.w);
                     s0 = fma(ea.x, b0, s0); t0 = fma(wa.x, b0, t0);
                     s1 = fma(ea.y, b1, s1); t1 = fma(wa.y, b1, t1);
                     s0 = fma(eb.x, b2, s0); t0 = fma(wb.x, b2, t0);
@@ -1011,7 +1028,7 @@ __global__ void __launch_bounds__(256, 1) estep_kernel(const EstepParams P) {
                         const int k = lane + 32 * i;
                         double bk = 0.0;
                         if (k < K) {
-                            bk = ((double)tile[(size_t)v * TS + k] * eu[i]) * sc;
+                            bk = (beta_f2d(tile[(size_t)v * TS + k]) * eu[i]) * sc;
                             if (b0 == 0) {
                                 const double ph = bk * sqc;
                                 rowsum[i] += ph;

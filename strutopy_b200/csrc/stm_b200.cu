@@ -10,6 +10,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -504,6 +505,10 @@ int stm_set_corpus(stm_ctx* ctx, int64_t D, const int64_t* doc_ptr, const int32_
         });
         lc.smem_per_warp = (int)smem_per_warp_bytes(lc.n_cap, ctx->TS, ctx->K1, ctx->KPL);
         lc.warps = std::min(8, ctx->max_smem / lc.smem_per_warp);
+        if (const char* cap = getenv("STM_MAX_WARPS")) {  // development knob (occupancy experiments)
+            const int c = atoi(cap);
+            if (c >= 1) lc.warps = std::min(lc.warps, c);
+        }
         if (lc.warps < 1)
             return fail(ctx, STM_ERR_UNSUPPORTED,
                         "a document's beta tile (" + std::to_string(lc.smem_per_warp) +
