@@ -134,6 +134,11 @@ __device__ __forceinline__ double np_sign(double x) {
     return (x > 0.0) ? 1.0 : ((x < 0.0) ? -1.0 : 0.0);
 }
 
+// IEEE fp64 division / square root kept out of line in the (scalar, warp-uniform) line-search code:
+// each inlined copy is ~25 instructions and the state machine has dozens of them (I-cache footprint).
+static __device__ __noinline__ double ddiv(double a, double b) { return a / b; }
+static __device__ __noinline__ double dsqrt(double a) { return sqrt(a); }
+
 // MINPACK-2 dcstep — scipy/optimize/_dcsrch.py:502-728.  The four cases share ONE copy of the cubic
 // interpolation arithmetic (theta, s, gamma, r): each case performs exactly the operations of the
 // SciPy source in the same order, only the operands are selected first (instruction footprint).
@@ -152,11 +157,12 @@ static __device__ __noinline__ void dcstep(double& stx, double& fx, double& dx, 
         const double f1 = (cs == 4) ? fp : fx, f2 = (cs == 4) ? fy : fp;
         const double s2 = (cs == 4) ? sty : stp, s1 = (cs == 4) ? stp : stx;
         const double d1 = (cs == 4) ? dy : dx;
-        const double theta = 3.0 * (f1 - f2) / (s2 - s1) + d1 + dp;
+        const double theta = ddiv(3.0 * (f1 - f2), s2 - s1) + d1 + dp;
         const double s = py_max3(fabs(theta), fabs(d1), fabs(dp));
-        double arg = (theta / s) * (theta / s) - (d1 / s) * (dp / s);
+        const double ts = ddiv(theta, s);
+        double arg = ts * ts - ddiv(d1, s) * ddiv(dp, s);
         if (cs == 3) arg = py_max2(0.0, arg);
-        double gamma = s * sqrt(arg);
+        double gamma = s * dsqrt(arg);
         const bool flip = (cs == 1) ? (stp < stx) : ((cs == 4) ? (stp > sty) : (stp > stx));
         if (flip) gamma = -gamma;
         double p, q;
@@ -164,17 +170,17 @@ static __device__ __noinline__ void dcstep(double& stx, double& fx, double& dx, 
         else if (cs == 2) { p = (gamma - dp) + theta; q = ((gamma - dp) + gamma) + dx; }
         else if (cs == 3) { p = (gamma - dp) + theta; q = (gamma + (dx - dp)) + gamma; }
         else { p = (gamma - dp) + theta; q = ((gamma - dp) + gamma) + dy; }
-        const double r = p / q;
+        const double r = ddiv(p, q);
         if (cs == 1) {
             const double stpc = stx + r * (stp - stx);
-            const double stpq = stx + ((dx / ((fx - fp) / (stp - stx) + dx)) / 2.0) * (stp - stx);
+            const double stpq = stx + (ddiv(dx, ddiv(fx - fp, stp - stx) + dx) * 0.5) * (stp - stx);
             if (fabs(stpc - stx) <= fabs(stpq - stx)) stpf = stpc;
-            else stpf = stpc + (stpq - stpc) / 2.0;
+            else stpf = stpc + (stpq - stpc) * 0.5;
             brackt = 1;
         } else if (cs == 4) {
             stpf = stp + r * (sty - stp);
         } else {
-            const double stpq = stp + (dp / (dp - dx)) * (stx - stp);
+            const double stpq = stp + ddiv(dp, dp - dx) * (stx - stp);
             if (cs == 2) {
                 const double stpc = stp + r * (stx - stp);
                 if (fabs(stpc - stp) > fabs(stpq - stp)) stpf = stpc;
@@ -219,20 +225,20 @@ static __device__ __noinline__ double cubicmin(double a, double fa, double fpa, 
     double A = __dadd_rn(__dmul_rn(d00, v0), __dmul_rn(d01, v1));
     double B = __dadd_rn(__dmul_rn(d10, v0), __dmul_rn(d11, v1));
     if (denom == 0.0) return nan("");
-    A /= denom;
-    B /= denom;
+    A = ddiv(A, denom);
+    B = ddiv(B, denom);
     const double radical = __dadd_rn(__dmul_rn(B, B), -__dmul_rn(3.0 * A, C));
     if (radical < 0.0 || A == 0.0) return nan("");
-    const double xmin = a + (-B + sqrt(radical)) / (3.0 * A);
+    const double xmin = a + ddiv(-B + dsqrt(radical), 3.0 * A);
     if (!isfinite(xmin)) return nan("");
     return xmin;
 }
 static __device__ __noinline__ double quadmin(double a, double fa, double fpa, double b, double fb) {
     const double D = fa, C = fpa, db = b - a * 1.0;
     if (db * db == 0.0) return nan("");
-    const double B = __dadd_rn(__dadd_rn(fb, -D), -__dmul_rn(C, db)) / (db * db);
+    const double B = ddiv(__dadd_rn(__dadd_rn(fb, -D), -__dmul_rn(C, db)), db * db);
     if (2.0 * B == 0.0) return nan("");
-    const double xmin = a - C / (2.0 * B);
+    const double xmin = a - ddiv(C, 2.0 * B);
     if (!isfinite(xmin)) return nan("");
     return xmin;
 }
@@ -628,7 +634,7 @@ __global__ void __launch_bounds__(256, 1) estep_kernel(const EstepParams P) {
                     const double cnt = red[0];
                     double ssum = red[1];
                     const double se_all = ssum + cnt;
-                    if (ssum != 0.0) ssum = ssum / cnt;
+                    if (ssum != 0.0 && cnt != 1.0) ssum = ddiv(ssum, cnt);
                     // scipy.special.logsumexp (scipy/special/_logsumexp.py:201-247)
                     const double lse = log_noinline(1.0 + ssum) + ((cnt == 1.0) ? 0.0 : log_noinline(cnt)) + m;
                     const double quad = 0.5 * red[2];
@@ -636,7 +642,7 @@ __global__ void __launch_bounds__(256, 1) estep_kernel(const EstepParams P) {
                     f_eval = quad - (data - Nint * lse);
 
                     // gradient stm.py:946-958 (beta NOT weighted by exp(eta): reference quirk)
-                    const double scale = Nsum / se_all;
+                    const double scale = ddiv(Nsum, se_all);
 #pragma unroll
                     for (int i = 0; i < KPL; ++i) {
                         const int k = lane + 32 * i;
@@ -669,7 +675,7 @@ __global__ void __launch_bounds__(256, 1) estep_kernel(const EstepParams P) {
                     n2 += g[i] * g[i];
                     gm = nanmax(gm, fabs(g[i]));
                 }
-                old_old_fval = old_fval + sqrt(warp_sum(n2)) / 2.0;
+                old_old_fval = old_fval + dsqrt(warp_sum(n2)) * 0.5;
                 gnorm = warp_max(gm);
                 new_iter = 1;
             } else if (ls == LS_W1) {
@@ -759,7 +765,7 @@ __global__ void __launch_bounds__(256, 1) estep_kernel(const EstepParams P) {
             if (start_w2) {
                 // scalar_search_wolfe2 prologue (scipy/optimize/_linesearch.py:395-409)
                 double alpha1;
-                if (derphi0 != 0.0) alpha1 = py_min2(1.0, 1.01 * 2 * (old_fval - old_old_fval) / derphi0);
+                if (derphi0 != 0.0) alpha1 = py_min2(1.0, ddiv(1.01 * 2 * (old_fval - old_old_fval), derphi0));
                 else alpha1 = 1.0;
                 if (alpha1 < 0.0) alpha1 = 1.0;
                 alpha1 = py_min2(alpha1, 1e100);
@@ -818,7 +824,7 @@ __global__ void __launch_bounds__(256, 1) estep_kernel(const EstepParams P) {
                 else if (!isfinite(old_fval)) { warnflag = 2; done = 1; }
                 else {
                     const double rhok_inv = warp_sum(ys_l);
-                    const double rho = (rhok_inv == 0.0) ? 1000.0 : 1.0 / rhok_inv;
+                    const double rho = (rhok_inv == 0.0) ? 1000.0 : ddiv(1.0, rhok_inv);
                     // Hk <- (I - rho s y')(Hk)(I - rho y s') + rho s s'   as a symmetric rank-2 update:
                     //   u = Hk y ;  Hk' = Hk - (rho u) s' - s (rho u)' + (rho^2 y'u + rho) s s'
                     double u[KPL];
@@ -891,13 +897,13 @@ __global__ void __launch_bounds__(256, 1) estep_kernel(const EstepParams P) {
                     // scalar_search_wolfe1 prologue + DCSRCH START
                     double alpha1;
                     if (derphi0 != 0.0) {
-                        alpha1 = py_min2(1.0, 1.01 * 2 * (old_fval - old_old_fval) / derphi0);
+                        alpha1 = py_min2(1.0, ddiv(1.01 * 2 * (old_fval - old_old_fval), derphi0));
                         if (alpha1 < 0.0) alpha1 = 1.0;
                     } else alpha1 = 1.0;
                     if (alpha1 < stpmin || alpha1 > stpmax || derphi0 >= 0.0 || !isfinite(alpha1)) {
                         // task = ERROR -> stp None -> wolfe2
                         double a1;
-                        if (derphi0 != 0.0) a1 = py_min2(1.0, 1.01 * 2 * (old_fval - old_old_fval) / derphi0);
+                        if (derphi0 != 0.0) a1 = py_min2(1.0, ddiv(1.01 * 2 * (old_fval - old_old_fval), derphi0));
                         else a1 = 1.0;
                         if (a1 < 0.0) a1 = 1.0;
                         a1 = py_min2(a1, 1e100);
@@ -906,7 +912,7 @@ __global__ void __launch_bounds__(256, 1) estep_kernel(const EstepParams P) {
                         ls = LS_W2;
                     } else {
                         brackt = 0; stage = 1; finit = old_fval; ginit = derphi0; gtest = c1 * ginit;
-                        width = stpmax - stpmin; width1 = width / 0.5;
+                        width = stpmax - stpmin; width1 = width * 2.0;
                         stx = 0.0; fx = finit; gx = ginit; sty = 0.0; fy = finit; gy = ginit;
                         stmin = 0.0; stmax = alpha1 + 4.0 * alpha1;
                         w1_it = 1;  // the START call was iteration 0 of DCSRCH.__call__
