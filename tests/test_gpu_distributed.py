@@ -1,0 +1,67 @@
+"""2-GPU data-parallel EM (NCCL) against the single-GPU run: skipped when fewer than 2 GPUs."""
+import os
+import socket
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from conftest import ROOT
+
+pytestmark = pytest.mark.gpu
+
+_WORKER = r"""
+import os, sys
+sys.path.insert(0, {root!r}); sys.path.insert(0, os.path.join({root!r}, 'tests'))
+import numpy as np, torch, torch.distributed as dist
+from conftest import load_golden
+from strutopy_b200 import STM
+rank = int(os.environ['RANK']); torch.cuda.set_device(rank)
+dist.init_process_group('nccl', device_id=torch.device('cuda', rank))
+g = load_golden('em_c1.npz'); K, V = int(g['K']), int(g['V'])
+docs = (g['doc_ptr'], g['word_id'], g['count'])
+def fit(distributed):
+    m = STM(docs, range(V), False, K, g['X'], False, 6, 0, 0.0, init_type='random', model_type='STM',
+            device=rank, distributed=distributed)
+    m.beta = g['beta0']
+    m.expectation_maximization(saving=False)
+    return m
+md = fit(True)
+ms = fit(False)
+assert md.N_local < md.N and md.N == ms.N
+rel = np.abs((np.array(md.last_bounds) - np.array(ms.last_bounds)) / np.array(ms.last_bounds))
+assert len(md.last_bounds) == 6 and rel.max() < 1e-6, rel          # summation order differs; EM amplifies
+assert rel[0] < 1e-12, rel
+ref = g['bounds'][:6]
+assert np.abs((np.array(md.last_bounds) - ref) / ref).max() < 1e-4
+np.testing.assert_allclose(md.theta, ms.theta, atol=1e-4)            # gathered over ranks
+np.testing.assert_allclose(md.beta, ms.beta, atol=1e-6)
+np.testing.assert_allclose(md.gamma, ms.gamma, atol=1e-5)
+np.testing.assert_allclose(md.sigma, ms.sigma, atol=1e-6)
+bss, sss = md.E_step(); md.M_step(bss, sss)
+bs2, ss2 = ms.E_step(); ms.M_step(bs2, ss2)
+np.testing.assert_allclose(bss, bs2, atol=1e-5); np.testing.assert_allclose(md.sigma, ms.sigma, atol=1e-6)
+dist.barrier(); dist.destroy_process_group()
+print('rank', rank, 'ok')
+"""
+
+
+def test_two_gpu_em_matches_single_gpu(tmp_path):
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    script = tmp_path / "worker.py"
+    script.write_text(_WORKER.format(root=ROOT))
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    procs = []
+    for r in range(2):
+        env = dict(os.environ, RANK=str(r), LOCAL_RANK=str(r), WORLD_SIZE="2", MASTER_ADDR="127.0.0.1",
+                   MASTER_PORT=str(port))
+        procs.append(subprocess.Popen([sys.executable, str(script)], env=env, stdout=subprocess.PIPE,
+                                      stderr=subprocess.STDOUT, text=True))
+    for pr in procs:
+        out, _ = pr.communicate(timeout=600)
+        assert pr.returncode == 0, out[-4000:]
