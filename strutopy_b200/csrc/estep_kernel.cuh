@@ -36,6 +36,22 @@
 #ifndef STM_LOG_NOINLINE
 #define STM_LOG_NOINLINE 1 // keep log()/exp() slow paths out of line (I-cache footprint)
 #endif
+// development-only switches for time attribution (results are WRONG when any is set)
+#ifndef STM_DBG_NO_PHI
+#define STM_DBG_NO_PHI 0
+#endif
+#ifndef STM_DBG_SKIP_POST
+#define STM_DBG_SKIP_POST 0
+#endif
+#ifndef STM_DBG_SKIP_BFGS
+#define STM_DBG_SKIP_BFGS 0
+#endif
+#ifndef STM_DBG_TIMING
+#define STM_DBG_TIMING 0   // 1: accumulate clock64() per phase into P.dbg_cycles[8] (variant builds only)
+#endif
+#ifndef STM_DBG_SKIP_DENSE
+#define STM_DBG_SKIP_DENSE 0
+#endif
 #define STM_PRAGMA2_(x) _Pragma(#x)
 #define STM_PRAGMA_(x) STM_PRAGMA2_(x)
 #if STM_Q_UNROLL > 0
@@ -83,7 +99,15 @@ struct EstepParams {
     // shared memory geometry
     int n_cap;                  // tile rows (words) per warp
     int smem_per_warp;          // bytes
+    unsigned long long* dbg_cycles;  // [8] phase cycle counters (only written when STM_DBG_TIMING)
 };
+#if STM_DBG_TIMING
+#define STM_T(var) const long long var = clock64()
+#define STM_TACC(slot, t0, t1) dbg_t[slot] += (t1) - (t0)
+#else
+#define STM_T(var)
+#define STM_TACC(slot, t0, t1)
+#endif
 
 #define STM_FULL 0xffffffffu
 
@@ -255,6 +279,15 @@ __device__ __forceinline__ double beta_f2d(float f) {
 #else
     return (double)f;
 #endif
+}
+
+// runtime-indexed read of a small register array (compiles to a select chain; multi-pass DMMA only)
+template <int N>
+__device__ __forceinline__ double fr_sel(const double (&fr)[N], int idx) {
+    double r = fr[0];
+#pragma unroll
+    for (int t = 1; t < N; ++t) r = (idx == t) ? fr[t] : r;
+    return r;
 }
 
 // log() kept out of line: it is only needed once per lane per evaluation (see logprod_*), so one
@@ -456,6 +489,9 @@ __global__ void __launch_bounds__(256, 1) estep_kernel(const EstepParams P) {
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     __syncwarp();
     uint32_t parity = 0;
+#if STM_DBG_TIMING
+    long long dbg_t[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+#endif
 
     const int gwarp = blockIdx.x * (blockDim.x >> 5) + warp;
     double* Hk = P.scratch + (size_t)gwarp * P.scratch_stride;  // BFGS inverse Hessian [K1][K1]
@@ -476,6 +512,7 @@ __global__ void __launch_bounds__(256, 1) estep_kernel(const EstepParams P) {
         if (lane == 0) qi = (int)atomicAdd(P.queue, 1u);
         qi = __shfl_sync(STM_FULL, qi, 0);
         if (qi >= P.n_docs) break;
+        STM_T(t_doc0);
         const int d = P.docs[qi];
         const long long p0 = P.doc_ptr[d];
         const int n = (int)(P.doc_ptr[d + 1] - p0);
@@ -499,13 +536,13 @@ __global__ void __launch_bounds__(256, 1) estep_kernel(const EstepParams P) {
         const double Nsum = warp_sum(nsum_l);           // np.sum(word_count)       stm.py:955
         const double Nint = (double)(long long)Nsum;    // int(np.sum(word_count))  stm.py:933
 
-        double x[KPL], mu[KPL], p[KPL], g[KPL], gt[KPL], xt[KPL], a[KPL], ex[KPL];
+        double x[KPL], mu[KPL], p[KPL], g[KPL], gt[KPL], xt[KPL], a[KPL], ex[KPL], xt2[KPL], gt2[KPL];
 #pragma unroll
         for (int i = 0; i < KPL; ++i) {
             const int k = lane + 32 * i;
             x[i] = (k < K1) ? P.eta[(size_t)d * K1 + k] : 0.0;
             mu[i] = (k < K1) ? P.mu[(size_t)d * K1 + k] : 0.0;
-            p[i] = 0.0; g[i] = 0.0; gt[i] = 0.0; xt[i] = 0.0; a[i] = 0.0; ex[i] = 0.0;
+            p[i] = 0.0; g[i] = 0.0; gt[i] = 0.0; xt[i] = 0.0; a[i] = 0.0; ex[i] = 0.0; xt2[i] = 0.0; gt2[i] = 0.0;
         }
         mbar_wait(mbar, parity);
         parity ^= 1;
@@ -536,11 +573,14 @@ __global__ void __launch_bounds__(256, 1) estep_kernel(const EstepParams P) {
         // BFGS (scipy/optimize/_optimize.py:1345-1526) as a warp-uniform state machine with ONE
         // objective-evaluation site.  Every evaluation returns f, the gradient gt and dphi = gt.p.
         // =======================================================================================
+        STM_T(t_bfgs0);
+        STM_TACC(0, t_doc0, t_bfgs0);   // slot 0: gather + a_k
         int ls = LS_INIT, k_it = 0, warnflag = 0, nfev = 0, done = 0;
         const int maxiter = K1 * 200;
         double alpha = 0.0, f_eval = 0.0, dphi = 0.0;
         double old_fval = 0.0, old_old_fval = 0.0, gnorm = 0.0, derphi0 = 0.0;
-        int have_cache = 0;
+        int have_cache = 0, have_cache2 = 0;
+        double f2 = 0.0;
         // dcsrch state
         int brackt = 0, stage = 1, w1_it = 0;
         double finit = 0, ginit = 0, gtest = 0, width = 0, width1 = 0;
@@ -552,19 +592,39 @@ __global__ void __launch_bounds__(256, 1) estep_kernel(const EstepParams P) {
 
         const double c1 = 1e-4, c2 = 0.9, xtol = 1e-14, stpmin = 1e-100, stpmax = 1e100;
 
+        if (STM_DBG_SKIP_BFGS) done = 1;
         while (!done) {
             // ---------------- evaluate f, g at x + alpha p --------------------------------------
+            STM_T(t_ev0);
             {
                 double xn[KPL];
-                bool same = have_cache;
+                bool same0 = have_cache, same1 = have_cache2;
 #pragma unroll
                 for (int i = 0; i < KPL; ++i) {
                     xn[i] = __dadd_rn(x[i], __dmul_rn(alpha, p[i]));
-                    same = same && (xn[i] == xt[i]);
+                    same0 = same0 && (xn[i] == xt[i]);
+                    same1 = same1 && (xn[i] == xt2[i]);
                 }
-                // ScalarFunction memoisation (scipy/_differentiable_functions.py:391-401):
-                // an identical trial point re-uses f and g
-                if (!__all_sync(STM_FULL, same)) {
+                // Memoisation.  SciPy's ScalarFunction re-uses f and g for a trial point identical to
+                // the LAST one (scipy/_differentiable_functions.py:391-401); f is deterministic, so
+                // re-using the last TWO points is value-identical and removes the A,B,A,B,... tail of
+                // a collapsing dcsrch interval (~20 % of all evaluations).
+                const bool hit0 = __all_sync(STM_FULL, same0);
+                const bool hit1 = !hit0 && __all_sync(STM_FULL, same1);
+                if (hit1) {
+#pragma unroll
+                    for (int i = 0; i < KPL; ++i) {
+                        const double tx = xt[i]; xt[i] = xt2[i]; xt2[i] = tx;
+                        const double tg = gt[i]; gt[i] = gt2[i]; gt2[i] = tg;
+                    }
+                    const double tf = f_eval; f_eval = f2; f2 = tf;
+                    have_cache2 = have_cache;  // both valid after a swap
+                }
+                if (!hit0 && !hit1) {
+#pragma unroll
+                    for (int i = 0; i < KPL; ++i) { xt2[i] = xt[i]; gt2[i] = gt[i]; }
+                    f2 = f_eval;
+                    have_cache2 = have_cache;
                     nfev++;
                     have_cache = 1;
                     double et[KPL];
@@ -577,6 +637,8 @@ __global__ void __launch_bounds__(256, 1) estep_kernel(const EstepParams P) {
                         m = nanmax(m, et[i]);
                     }
                     m = warp_max(m);
+                    STM_T(t_e1);
+                    STM_TACC(8, t_ev0, t_e1);       // slot 8: memo check + max reduce
                     // red[]: cnt, ssum, quad, data, (S d - a).p, ex.p  — reduced together after the contraction
                     double red[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
 #pragma unroll
@@ -592,6 +654,8 @@ __global__ void __launch_bounds__(256, 1) estep_kernel(const EstepParams P) {
                     }
                     __syncwarp();
 
+                    STM_T(t_e2);
+                    STM_TACC(9, t_e1, t_e2);        // slot 9: exp + partials + sync
                     // data term: sum_v c_v (m + log(sum_k e_k beta_kv))           stm.py:938-941
                     LogProd lp;
                     logprod_init(lp);
@@ -629,8 +693,14 @@ __global__ void __launch_bounds__(256, 1) estep_kernel(const EstepParams P) {
                         }
                         logprod_renorm(lp);
                     }
+                    STM_T(t_e3);
+                    STM_TACC(10, t_e2, t_e3);       // slot 10: contraction + logprod accumulate
                     red[3] = logprod_value(lp);
+                    STM_T(t_e4);
+                    STM_TACC(11, t_e3, t_e4);       // slot 11: log of the product
                     warp_sum_n<6>(red);
+                    STM_T(t_e5);
+                    STM_TACC(12, t_e4, t_e5);       // slot 12: batched reduction
                     const double cnt = red[0];
                     double ssum = red[1];
                     const double se_all = ssum + cnt;
@@ -650,6 +720,8 @@ __global__ void __launch_bounds__(256, 1) estep_kernel(const EstepParams P) {
                         gt[i] = (k < K1) ? (Sd[i] * dk - (a[i] - scale * ex[i])) : 0.0;
                     }
                     dphi = red[4] + scale * red[5];   // = gt . p
+                    STM_T(t_e6);
+                    STM_TACC(13, t_e5, t_e6);       // slot 13: lse + f + gradient
                 } else {
                     double dp_l2 = 0.0;
 #pragma unroll
@@ -659,6 +731,8 @@ __global__ void __launch_bounds__(256, 1) estep_kernel(const EstepParams P) {
             }
 
             // ---------------- consume the evaluation --------------------------------------------
+            STM_T(t_ev1);
+            STM_TACC(1, t_ev0, t_ev1);      // slot 1: evaluation (incl. memo check)
             int accept = 0;      // 1: step alpha accepted (f_eval, gt valid)
             int fail = 0;        // 1: line search failed
             int new_iter = 0;    // 1: start a new BFGS iteration (compute p, init wolfe1)
@@ -798,6 +872,8 @@ __global__ void __launch_bounds__(256, 1) estep_kernel(const EstepParams P) {
             }
 
             if (fail) { warnflag = 2; done = 1; }
+            STM_T(t_ls1);
+            STM_TACC(2, t_ev1, t_ls1);      // slot 2: line-search logic
 
             if (accept) {
                 // _minimize_bfgs body after the line search (scipy/optimize/_optimize.py:1452-1498)
@@ -921,7 +997,11 @@ __global__ void __launch_bounds__(256, 1) estep_kernel(const EstepParams P) {
                     }
                 }
             }
+#if STM_DBG_TIMING
+            { const long long t_it1 = clock64(); dbg_t[3] += t_it1 - t_ls1; }  // slot 3: accept / H update / new iteration
+#endif
         }  // BFGS loop
+        STM_T(t_post0);
 
         int status = warnflag;
         if (status != 2) {
@@ -966,7 +1046,10 @@ __global__ void __launch_bounds__(256, 1) estep_kernel(const EstepParams P) {
             }
             __syncwarp();
         }
+        if (STM_DBG_SKIP_POST) { if (lane == 0) { P.doc_bound[d] = 0.0; P.doc_info[d] = status; P.doc_nfev[d] = nfev; } continue; }
         // colsum_v = sum_k e_k beta_kv and the log-likelihood part of the bound (stm.py:1088-1096)
+        STM_T(t_p1);
+        STM_TACC(4, t_post0, t_p1);         // slot 4: status, theta
         double loglik;
         {
             LogProd lp;
@@ -998,73 +1081,102 @@ __global__ void __launch_bounds__(256, 1) estep_kernel(const EstepParams P) {
         }
         __syncwarp();
 
-        // Hessian data term  sum_v b_v b_v'  with b_kv = beta_kv e_k sqrt(c_v)/colsum_v (stm.py:1000-1006),
-        // accumulated in BSxBS register blocks of the lower triangle; phi_kv = b_kv sqrt(c_v) is
-        // scattered into beta_ss on the way (stm.py:1103-1118, 582-590).
+        // Hessian data term  sum_v b_v b_v'  with b_kv = beta_kv e_k sqrt(c_v)/colsum_v (stm.py:1000-1006)
+        // on the fp64 tensor cores: mma.sync m8n8k4 (DMMA), four words per step.  Lane (w = lane&3,
+        // kk = lane>>2) computes b for word v0+w and topics 8t+kk: exactly its A-fragment element of
+        // row-block t AND its B-fragment element of column-block t, so no staging and no barrier.
+        // phi_kv = b_kv sqrt(c_v) is scattered into beta_ss on the way (stm.py:1103-1118, 582-590).
         double rowsum[KPL];  // sum_v phi_kv  (np.sum(c, axis=1), stm.py:1011)
-#pragma unroll
-        for (int i = 0; i < KPL; ++i) rowsum[i] = 0.0;
         {
-            constexpr int BS = (KPL == 1) ? 4 : 8;
-            const int nb = (K1 + BS - 1) / BS;
-            const int nblk = nb * (nb + 1) / 2;
+            constexpr int NBMAX = 4 * KPL;                 // 8-topic blocks covering K <= 32*KPL
+            constexpr int RB = (KPL <= 2) ? NBMAX : ((KPL == 3) ? 3 : 2);  // block rows per pass
+            const int nb = (K1 + 7) >> 3;                  // block rows/cols of the (K-1)x(K-1) matrix
+            const int w4 = lane & 3, kk = lane >> 2;
             double* beta_ss_a = P.beta_ss_t + (size_t)asp * P.V * TS;
-            for (int b0 = 0; b0 < nblk; b0 += 32) {
-                const int blk = b0 + lane;
-                // block index -> (br, bc) with bc <= br
-                int br = 0, bc = 0;
-                if (blk < nblk) {
-                    br = (int)((sqrt(8.0 * blk + 1.0) - 1.0) * 0.5);
-                    while ((br + 1) * (br + 2) / 2 <= blk) br++;
-                    while (br * (br + 1) / 2 > blk) br--;
-                    bc = blk - br * (br + 1) / 2;
-                }
-                double acc[BS][BS];
+            double rs[NBMAX];
 #pragma unroll
-                for (int r = 0; r < BS; ++r)
+            for (int t = 0; t < NBMAX; ++t) rs[t] = 0.0;
+#pragma unroll 1
+            for (int r0 = 0; r0 < nb; r0 += RB) {
+                double acc[RB][NBMAX][2];
 #pragma unroll
-                    for (int c = 0; c < BS; ++c) acc[r][c] = 0.0;
-                double* bbuf = v2;  // [2][KVS] double-buffered b vector (v2, v3 contiguous)
-                for (int v = 0; v < n; ++v) {
-                    double* bv = bbuf + (v & 1) * KVS;
-                    const double sc = wv[v];
-                    const double sqc = wv2[v];
+                for (int rr = 0; rr < RB; ++rr)
 #pragma unroll
-                    for (int i = 0; i < KPL; ++i) {
-                        const int k = lane + 32 * i;
+                    for (int bc = 0; bc < NBMAX; ++bc) { acc[rr][bc][0] = 0.0; acc[rr][bc][1] = 0.0; }
+#pragma unroll 1
+                for (int vb = 0; vb < n; vb += 4) {
+                    const int v = vb + w4;
+                    const bool vok = v < n;
+                    const int vc = vok ? v : 0;
+                    const double sc = vok ? wv[vc] : 0.0;
+                    const double sqc = wv2[vc];
+                    const float* trow = tile + (size_t)vc * TS;
+                    double* ssrow = beta_ss_a + (size_t)wid[vc] * TS;
+                    double fr[NBMAX];
+#pragma unroll
+                    for (int t = 0; t < NBMAX; ++t) {
+                        const int k = 8 * t + kk;
                         double bk = 0.0;
                         if (k < K) {
-                            bk = (beta_f2d(tile[(size_t)v * TS + k]) * eu[i]) * sc;
-                            if (b0 == 0) {
+                            bk = (beta_f2d(trow[k]) * v0[k]) * sc;
+                            if (r0 == 0 && vok) {
                                 const double ph = bk * sqc;
-                                rowsum[i] += ph;
-                                red_add_f64(beta_ss_a + (size_t)wid[v] * TS + k, ph);
+                                rs[t] += ph;
+                                if (!STM_DBG_NO_PHI) red_add_f64(ssrow + k, ph);
                             }
                         }
-                        bv[k] = bk;
+                        fr[t] = bk;
                     }
-                    __syncwarp();
-                    if (blk < nblk) {
-                        double rv[BS], cv[BS];
 #pragma unroll
-                        for (int r = 0; r < BS; ++r) { rv[r] = bv[br * BS + r]; cv[r] = bv[bc * BS + r]; }
+                    for (int rr = 0; rr < RB; ++rr) {
+                        const int br = r0 + rr;
 #pragma unroll
-                        for (int r = 0; r < BS; ++r)
-#pragma unroll
-                            for (int c = 0; c < BS; ++c) acc[r][c] = fma(rv[r], cv[c], acc[r][c]);
+                        for (int bc = 0; bc < NBMAX; ++bc) {
+                            // single pass (KPL <= 2): br == rr at compile time, the upper blocks vanish
+                            if ((KPL <= 2) ? (bc <= rr) : true) {
+                                if (br < nb && bc <= br) {
+                                    const double af = (KPL <= 2) ? fr[rr] : fr_sel<NBMAX>(fr, br);
+                                    asm volatile(
+                                        "mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                                        : "+d"(acc[rr][bc][0]), "+d"(acc[rr][bc][1])
+                                        : "d"(af), "d"(fr[bc]));
+                                }
+                            }
+                        }
                     }
                 }
-                __syncwarp();
-                if (blk < nblk) {
+                // C fragment: row = lane>>2, cols = 2*(lane&3) + {0,1}
 #pragma unroll
-                    for (int r = 0; r < BS; ++r)
+                for (int rr = 0; rr < RB; ++rr) {
+                    const int br = r0 + rr;
 #pragma unroll
-                        for (int c = 0; c < BS; ++c) {
-                            const int gi = br * BS + r, gj = bc * BS + c;
-                            if (gi < K1 && gj < K1 && gj <= gi) Hg[(size_t)gi * K1 + gj] = acc[r][c];
+                    for (int bc = 0; bc < NBMAX; ++bc) {
+                        if ((KPL <= 2) ? (bc <= rr) : true) {
+                            if (br < nb && bc <= br) {
+                                const int gi = br * 8 + kk;
+#pragma unroll
+                                for (int c = 0; c < 2; ++c) {
+                                    const int gj = bc * 8 + 2 * w4 + c;
+                                    if (gi < K1 && gj <= gi) Hg[(size_t)gi * K1 + gj] = acc[rr][bc][c];
+                                }
+                            }
                         }
+                    }
                 }
             }
+            // rowsum_k: add the 4 word slots (lanes sharing kk), publish, re-read lane-distributed
+#pragma unroll
+            for (int t = 0; t < NBMAX; ++t) {
+                rs[t] += __shfl_xor_sync(STM_FULL, rs[t], 1);
+                rs[t] += __shfl_xor_sync(STM_FULL, rs[t], 2);
+            }
+            __syncwarp();
+#pragma unroll
+            for (int t = 0; t < NBMAX; ++t)
+                if (w4 == 0 && 8 * t + kk < KV) v1[8 * t + kk] = rs[t];
+            __syncwarp();
+#pragma unroll
+            for (int i = 0; i < KPL; ++i) rowsum[i] = v1[lane + 32 * i];
         }
         __syncwarp();
         __threadfence_block();
@@ -1093,6 +1205,9 @@ __global__ void __launch_bounds__(256, 1) estep_kernel(const EstepParams P) {
         // PD test + repairs (stm.py:1017-1021, 1039-1048).  "all eigenvalues > 0" is restated as
         // "Cholesky succeeds".  The factor overwrites the strict lower triangle + a separate diagonal
         // so the matrix can be restored from its upper triangle for the retries.
+        if (STM_DBG_SKIP_DENSE) { if (lane == 0) { P.doc_bound[d] = 0.0; P.doc_info[d] = status; P.doc_nfev[d] = nfev; } continue; }
+        STM_T(t_p2);
+        STM_TACC(5, t_p1, t_p2);            // slot 5: colsum + Hessian (DMMA) + assemble
         int repair = 0;
         double* Ld = v2;      // diagonal of L
         double* Dg = v3;      // diagonal of H (original / repaired)
@@ -1134,6 +1249,8 @@ __global__ void __launch_bounds__(256, 1) estep_kernel(const EstepParams P) {
         }
         __syncwarp();
 
+        STM_T(t_p3);
+        STM_TACC(6, t_p2, t_p3);            // slot 6: Cholesky + repairs
         // bound (stm.py:1085-1100)
         double det_l = 0.0, q_l = 0.0;
         for (int k = lane; k < K1; k += 32) det_l += log_noinline(Ld[k]);
@@ -1157,7 +1274,14 @@ __global__ void __launch_bounds__(256, 1) estep_kernel(const EstepParams P) {
             }
         }
         __syncwarp();
+#if STM_DBG_TIMING
+        { const long long t_p4 = clock64(); dbg_t[7] += t_p4 - t_p3; }   // slot 7: bound + inverse + nu
+#endif
     }  // document loop
+#if STM_DBG_TIMING
+    if (lane == 0)
+        for (int i = 0; i < 16; ++i) atomicAdd(P.dbg_cycles + i, (unsigned long long)dbg_t[i]);
+#endif
 }
 
 }  // namespace stm

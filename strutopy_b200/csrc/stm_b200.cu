@@ -42,6 +42,7 @@ struct stm_ctx {
     int* d_aspect = nullptr;
     std::vector<LengthClass> classes;
     unsigned int* d_queues = nullptr;
+    unsigned long long* d_dbg = nullptr;
     double* d_scratch = nullptr;
     long long scratch_stride = 0;
     int max_warps_total = 0;
@@ -377,6 +378,7 @@ void free_corpus(stm_ctx* c) {
     for (auto& lc : c->classes) cudaFree(lc.d_docs);
     c->classes.clear();
     cudaFree(c->d_queues); c->d_queues = nullptr;
+    cudaFree(c->d_dbg); c->d_dbg = nullptr;
     cudaFree(c->d_scratch); c->d_scratch = nullptr;
     cudaFree(c->d_sigma_rep); c->d_sigma_rep = nullptr;
     cudaFree(c->d_ones); c->d_ones = nullptr;
@@ -532,6 +534,8 @@ int stm_set_corpus(stm_ctx* ctx, int64_t D, const int64_t* doc_ptr, const int32_
         CU(cudaMemcpy(ctx->d_aspect, aspect, sizeof(int) * D, cudaMemcpyHostToDevice));
     }
     CU(cudaMalloc(&ctx->d_queues, sizeof(unsigned int) * 16));
+    CU(cudaMalloc(&ctx->d_dbg, sizeof(unsigned long long) * 16));
+    CU(cudaMemset(ctx->d_dbg, 0, sizeof(unsigned long long) * 16));
     ctx->max_warps_total = std::max(max_warps, 1);
     ctx->scratch_stride = 2LL * ctx->K1 * ctx->K1;
     CU(cudaMalloc(&ctx->d_scratch, sizeof(double) * ctx->scratch_stride * ctx->max_warps_total));
@@ -544,6 +548,15 @@ int stm_set_corpus(stm_ctx* ctx, int64_t D, const int64_t* doc_ptr, const int32_
     CU(cudaDeviceSynchronize());
     return STM_OK;
 }
+
+#if STM_DBG_TIMING
+// variant builds only (not part of include/stm_b200.h): read and reset the per-phase cycle counters
+int stm_dbg_cycles(stm_ctx* ctx, unsigned long long* out8) {
+    cudaMemcpy(out8, ctx->d_dbg, sizeof(unsigned long long) * 16, cudaMemcpyDeviceToHost);
+    cudaMemset(ctx->d_dbg, 0, sizeof(unsigned long long) * 16);
+    return 0;
+}
+#endif
 
 int stm_stats_layout(const stm_ctx* ctx, int p, int64_t* offsets) {
     if (!ctx || !offsets || p < 0) return STM_ERR_INVALID;
@@ -595,6 +608,7 @@ int stm_estep(stm_ctx* ctx, const float* beta_t_dev, const double* mu_dev, const
         P.sigma_ss_rep = ctx->d_sigma_rep; P.n_rep = ctx->n_rep;
         P.scratch = ctx->d_scratch; P.scratch_stride = ctx->scratch_stride;
         P.n_cap = lc.n_cap; P.smem_per_warp = lc.smem_per_warp;
+        P.dbg_cycles = ctx->d_dbg;
         const size_t smem = (size_t)lc.smem_per_warp * lc.warps;
         CU(launch_class(ctx->KPL, P, lc.J, lc.grid, lc.warps * 32, smem, st));
         ctx->launches++;

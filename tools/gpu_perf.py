@@ -46,6 +46,21 @@ def main():
         torch.cuda.synchronize()
         tm = time.perf_counter() - t
         d = m.doc_diagnostics()
+        try:
+            import ctypes as C
+            from strutopy_b200 import _lib as L_
+            fn = L_.load().stm_dbg_cycles
+            arr = (C.c_ulonglong * 16)()
+            fn(m._ctx.handle, arr)
+            tot = sum(arr[:8]) or 1
+            names = ["gather+a_k", "eval", "linesearch", "accept/Hupd", "theta", "colsum+hess", "chol", "bound+inv+nu",
+                     "e:memo+max", "e:exp", "e:contract+lp", "e:log(prod)", "e:reduce", "e:lse+grad", "-", "-"]
+            out.append("      cycles/doc/warp: " + "  ".join(f"{nm} {c/len(d['nfev']):.0f} ({c/tot*100:.0f}%)" for nm, c in zip(names, arr)))
+        except AttributeError:
+            pass
+        nf = d['nfev']
+        out.append(f"      nfev pct50/90/99/99.9/max {np.percentile(nf,50):.0f}/{np.percentile(nf,90):.0f}/{np.percentile(nf,99):.0f}/"
+                   f"{np.percentile(nf,99.9):.0f}/{nf.max()}  nit max {d['nit'].max()}  sum nfev {nf.sum()}  status {np.bincount(d['status'])}")
         out.append(f"it{it}: estep {e0.elapsed_time(e1):7.2f} ms  nfev {d['nfev'].mean():5.1f}  nit {d['nit'].mean():4.2f} "
                    f"repair {np.mean(d['repair'] > 0):.2f}  mstep {tm*1e3:5.2f} ms  bound {b:.6f}")
     print(f"== {a.tag}")
