@@ -1,5 +1,6 @@
-// estep_inst.cu — instantiates stm::estep_kernel<STM_KPL, J> for J in {2,4,5,8}; compiled once per
-// STM_KPL in {1,2,3,4} (K <= 32*STM_KPL) so the instantiations build in parallel.
+// estep_inst.cu — instantiates stm::bfgs_kernel<STM_KPL, J> for J in {2,4,5,8} and
+// stm::post_kernel<STM_KPL>; compiled once per STM_KPL in {1,2,3,4} (K <= 32*STM_KPL) so the
+// instantiations build in parallel.
 #include "estep_kernel.cuh"
 
 #ifndef STM_KPL
@@ -8,14 +9,14 @@
 #define STM_CAT2(a, b) a##b
 #define STM_CAT(a, b) STM_CAT2(a, b)
 
-cudaError_t STM_CAT(stm_launch_kpl, STM_KPL)(const stm::EstepParams& P, int J, int grid, int block,
-                                             size_t smem, cudaStream_t st) {
+cudaError_t STM_CAT(stm_launch_bfgs_kpl, STM_KPL)(const stm::EstepParams& P, int J, int grid, int block,
+                                                  size_t smem, cudaStream_t st) {
 #define STM_LAUNCH(JJ)                                                                                \
     {                                                                                                 \
-        cudaError_t e = cudaFuncSetAttribute(stm::estep_kernel<STM_KPL, JJ>,                          \
+        cudaError_t e = cudaFuncSetAttribute(stm::bfgs_kernel<STM_KPL, JJ>,                           \
                                              cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
         if (e != cudaSuccess) return e;                                                               \
-        stm::estep_kernel<STM_KPL, JJ><<<grid, block, smem, st>>>(P);                                 \
+        stm::bfgs_kernel<STM_KPL, JJ><<<grid, block, smem, st>>>(P);                                  \
         return cudaGetLastError();                                                                    \
     }
     switch (J) {
@@ -25,4 +26,13 @@ cudaError_t STM_CAT(stm_launch_kpl, STM_KPL)(const stm::EstepParams& P, int J, i
         default: STM_LAUNCH(8)
     }
 #undef STM_LAUNCH
+}
+
+cudaError_t STM_CAT(stm_launch_post_kpl, STM_KPL)(const stm::EstepParams& P, int grid, int block, size_t smem,
+                                                  cudaStream_t st) {
+    cudaError_t e = cudaFuncSetAttribute(stm::post_kernel<STM_KPL>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)smem);
+    if (e != cudaSuccess) return e;
+    stm::post_kernel<STM_KPL><<<grid, block, smem, st>>>(P);
+    return cudaGetLastError();
 }

@@ -52,6 +52,9 @@
 #ifndef STM_DBG_SKIP_DENSE
 #define STM_DBG_SKIP_DENSE 0
 #endif
+#ifndef STM_BFGS_MAX_THREADS
+#define STM_BFGS_MAX_THREADS 256   // launch bound of kernel A (register budget = 65536 / this)
+#endif
 #define STM_PRAGMA2_(x) _Pragma(#x)
 #define STM_PRAGMA_(x) STM_PRAGMA2_(x)
 #if STM_Q_UNROLL > 0
@@ -455,30 +458,39 @@ static __device__ __noinline__ void inverse_and_nu(double* Hm, const double* Ld,
 // status / repair codes mirror oracle/stm_oracle.h
 enum { LS_INIT = 0, LS_W1 = 1, LS_W2 = 2, LS_ZOOM = 3 };
 
+// ===== BFGS KERNEL =====
+// Line-search / BFGS scalars (warp-uniform) live in shared memory, not registers: the state machine
+// touches them only between evaluations, and the registers they would pin (~60) are what limits
+// the number of resident documents per SM.  Every lane writes the same value; reads are broadcasts.
+struct LsState {
+    double old_fval, old_old_fval, gnorm, derphi0, f2;
+    // dcsrch (scipy/optimize/_dcsrch.py)
+    double finit, ginit, gtest, width, width1, stx, fx, gx, sty, fy, gy, stmin, stmax;
+    // scalar_search_wolfe2 / _zoom (scipy/optimize/_linesearch.py)
+    double alpha0, phi_a0, derphi_a0, a_lo, a_hi, phi_lo, phi_hi, derphi_lo, phi_rec, a_rec;
+    int brackt, stage, w1_it, w2_i, z_i, pad_;
+};
+
+// Kernel A: per-document BFGS (stm.py:536-545 -> scipy.optimize.minimize(method="BFGS")).
+// Writes eta (in place), doc_info = status | nit << 4, doc_nfev.
 template <int KPL, int J>
-__global__ void __launch_bounds__(256, 1) estep_kernel(const EstepParams P) {
+__global__ void __launch_bounds__(STM_BFGS_MAX_THREADS, 1) bfgs_kernel(const EstepParams P) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
     const int K = P.K, K1 = K - 1, TS = P.TS;
     constexpr int KV = KPL * 32;
     constexpr int KVS = KV + 8;  // padded stride of the shared K-vectors (TS <= KV+4, block reads <= KV+6)
-    const int HS = K1 | 1;  // odd row stride (doubles) of the dense (K-1)x(K-1) matrices in smem
 
-    // ---- per-warp shared memory carve-up -----------------------------------------------------
+    // ---- per-warp shared memory carve-up (bfgs_smem_per_warp in stm_b200.cu mirrors this) -----
     unsigned char* base = smem_raw + (size_t)warp * P.smem_per_warp;
-    size_t tile_bytes = (size_t)P.n_cap * TS * 4;
-    const size_t h_bytes = (size_t)K1 * HS * 8;
-    if (h_bytes > tile_bytes) tile_bytes = h_bytes;
-    tile_bytes = (tile_bytes + 127) & ~(size_t)127;
+    const size_t tile_bytes = ((size_t)P.n_cap * TS * 4 + 127) & ~(size_t)127;
     float* tile = reinterpret_cast<float*>(base);
-    double* Hm = reinterpret_cast<double*>(base);  // aliases the tile once it is dead
-    double* wv = reinterpret_cast<double*>(base + tile_bytes);            // [n_cap] per-word fp64
-    double* wv2 = wv + P.n_cap;                                           // [n_cap] sqrt(c_v)
-    double* vec = wv2 + P.n_cap;                                          // [4][KVS]
-    float* cw = reinterpret_cast<float*>(vec + 4 * KVS);                  // [n_cap] counts
-    int* wid = reinterpret_cast<int*>(cw + P.n_cap);                      // [n_cap]
-    uint64_t* mbar = reinterpret_cast<uint64_t*>(wid + P.n_cap);
+    double* wv = reinterpret_cast<double*>(base + tile_bytes);            // [n_cap] c_v / colsum_v (a_k precompute)
+    double* vec = wv + P.n_cap;                                           // [4][KVS]
+    LsState& S = *reinterpret_cast<LsState*>(vec + 4 * KVS);
+    float* cw = reinterpret_cast<float*>(vec + 4 * KVS + sizeof(LsState) / 8);  // [n_cap] counts
+    uint64_t* mbar = reinterpret_cast<uint64_t*>(cw + ((P.n_cap + 1) & ~1));
     double* v0 = vec;            // e / broadcast scratch
     double* v1 = vec + KVS;
     double* v2 = vec + 2 * KVS;
@@ -495,8 +507,6 @@ __global__ void __launch_bounds__(256, 1) estep_kernel(const EstepParams P) {
 
     const int gwarp = blockIdx.x * (blockDim.x >> 5) + warp;
     double* Hk = P.scratch + (size_t)gwarp * P.scratch_stride;  // BFGS inverse Hessian [K1][K1]
-    double* Hg = Hk + (size_t)K1 * K1;                          // Laplace Hessian bounce [K1][K1]
-    double* sig_acc = P.sigma_ss_rep + (size_t)(gwarp % P.n_rep) * K1 * K1;
 
     // diagonal of siginv, lane-distributed
     double Sd[KPL];
@@ -505,7 +515,6 @@ __global__ void __launch_bounds__(256, 1) estep_kernel(const EstepParams P) {
         const int k = lane + 32 * i;
         Sd[i] = (k < K1) ? P.prior[k] : 0.0;
     }
-    const double sigmaentropy = P.prior[K1];
 
     for (;;) {
         int qi = 0;
@@ -528,7 +537,6 @@ __global__ void __launch_bounds__(256, 1) estep_kernel(const EstepParams P) {
         for (int v = lane; v < n; v += 32) {
             const int w = P.word_id[p0 + v];
             const float c = P.count[p0 + v];
-            wid[v] = w;
             cw[v] = c;
             nsum_l += (double)c;
             tma_row_g2s(tile + (size_t)v * TS, beta_a + (size_t)w * TS, (uint32_t)(TS * 4), mbar);
@@ -578,17 +586,12 @@ __global__ void __launch_bounds__(256, 1) estep_kernel(const EstepParams P) {
         int ls = LS_INIT, k_it = 0, warnflag = 0, nfev = 0, done = 0;
         const int maxiter = K1 * 200;
         double alpha = 0.0, f_eval = 0.0, dphi = 0.0;
-        double old_fval = 0.0, old_old_fval = 0.0, gnorm = 0.0, derphi0 = 0.0;
         int have_cache = 0, have_cache2 = 0;
-        double f2 = 0.0;
-        // dcsrch state
-        int brackt = 0, stage = 1, w1_it = 0;
-        double finit = 0, ginit = 0, gtest = 0, width = 0, width1 = 0;
-        double stx = 0, fx = 0, gx = 0, sty = 0, fy = 0, gy = 0, stmin = 0, stmax = 0;
-        // wolfe2 / zoom state
-        int w2_i = 0, z_i = 0;
-        double alpha0 = 0, phi_a0 = 0, derphi_a0 = 0;
-        double a_lo = 0, a_hi = 0, phi_lo = 0, phi_hi = 0, derphi_lo = 0, phi_rec = 0, a_rec = 0;
+        if (lane == 0) {
+            S.old_fval = 0.0; S.old_old_fval = 0.0; S.gnorm = 0.0; S.derphi0 = 0.0; S.f2 = 0.0;
+            S.brackt = 0; S.stage = 1; S.w1_it = 0; S.w2_i = 0; S.z_i = 0;
+        }
+        __syncwarp();
 
         const double c1 = 1e-4, c2 = 0.9, xtol = 1e-14, stpmin = 1e-100, stpmax = 1e100;
 
@@ -617,13 +620,13 @@ __global__ void __launch_bounds__(256, 1) estep_kernel(const EstepParams P) {
                         const double tx = xt[i]; xt[i] = xt2[i]; xt2[i] = tx;
                         const double tg = gt[i]; gt[i] = gt2[i]; gt2[i] = tg;
                     }
-                    const double tf = f_eval; f_eval = f2; f2 = tf;
+                    const double tf = f_eval; f_eval = S.f2; S.f2 = tf;
                     have_cache2 = have_cache;  // both valid after a swap
                 }
                 if (!hit0 && !hit1) {
 #pragma unroll
                     for (int i = 0; i < KPL; ++i) { xt2[i] = xt[i]; gt2[i] = gt[i]; }
-                    f2 = f_eval;
+                    S.f2 = f_eval;
                     have_cache2 = have_cache;
                     nfev++;
                     have_cache = 1;
@@ -741,7 +744,7 @@ __global__ void __launch_bounds__(256, 1) estep_kernel(const EstepParams P) {
             double zl = 0, zh = 0, zpl = 0, zph = 0, zdl = 0;
 
             if (ls == LS_INIT) {
-                old_fval = f_eval;
+                S.old_fval = f_eval;
                 double n2 = 0.0, gm = 0.0;
 #pragma unroll
                 for (int i = 0; i < KPL; ++i) {
@@ -749,124 +752,124 @@ __global__ void __launch_bounds__(256, 1) estep_kernel(const EstepParams P) {
                     n2 += g[i] * g[i];
                     gm = nanmax(gm, fabs(g[i]));
                 }
-                old_old_fval = old_fval + dsqrt(warp_sum(n2)) * 0.5;
-                gnorm = warp_max(gm);
+                S.old_old_fval = S.old_fval + dsqrt(warp_sum(n2)) * 0.5;
+                S.gnorm = warp_max(gm);
                 new_iter = 1;
             } else if (ls == LS_W1) {
                 // one DCSRCH._iterate (scipy/optimize/_dcsrch.py:310-500) with (stp=alpha, f, g)
                 const double stp_in = alpha, f = f_eval, gd = dphi;
-                const double ftest = finit + stp_in * gtest;
+                const double ftest = S.finit + stp_in * S.gtest;
                 int warn = 0;
-                if (stage == 1 && f <= ftest && gd >= 0.0) stage = 2;
-                if (brackt && (stp_in <= stmin || stp_in >= stmax)) warn = 1;
-                if (brackt && stmax - stmin <= xtol * stmax) warn = 1;
-                if (stp_in == stpmax && f <= ftest && gd <= gtest) warn = 1;
-                if (stp_in == stpmin && (f > ftest || gd >= gtest)) warn = 1;
-                if (f <= ftest && fabs(gd) <= c2 * -ginit) {
+                if (S.stage == 1 && f <= ftest && gd >= 0.0) S.stage = 2;
+                if (S.brackt && (stp_in <= S.stmin || stp_in >= S.stmax)) warn = 1;
+                if (S.brackt && S.stmax - S.stmin <= xtol * S.stmax) warn = 1;
+                if (stp_in == stpmax && f <= ftest && gd <= S.gtest) warn = 1;
+                if (stp_in == stpmin && (f > ftest || gd >= S.gtest)) warn = 1;
+                if (f <= ftest && fabs(gd) <= c2 * -S.ginit) {
                     accept = 1;
                 } else if (warn) {
                     start_w2 = 1;
                 } else {
                     double stp = stp_in;
-                    if (stage == 1 && f <= fx && f > ftest) {
-                        double fm = f - stp * gtest, fxm = fx - stx * gtest, fym = fy - sty * gtest;
-                        double gm = gd - gtest, gxm = gx - gtest, gym = gy - gtest;
-                        dcstep(stx, fxm, gxm, sty, fym, gym, stp, fm, gm, brackt, stmin, stmax);
-                        fx = fxm + stx * gtest; fy = fym + sty * gtest;
-                        gx = gxm + gtest; gy = gym + gtest;
+                    if (S.stage == 1 && f <= S.fx && f > ftest) {
+                        double fm = f - stp * S.gtest, fxm = S.fx - S.stx * S.gtest, fym = S.fy - S.sty * S.gtest;
+                        double gm = gd - S.gtest, gxm = S.gx - S.gtest, gym = S.gy - S.gtest;
+                        dcstep(S.stx, fxm, gxm, S.sty, fym, gym, stp, fm, gm, S.brackt, S.stmin, S.stmax);
+                        S.fx = fxm + S.stx * S.gtest; S.fy = fym + S.sty * S.gtest;
+                        S.gx = gxm + S.gtest; S.gy = gym + S.gtest;
                     } else {
-                        dcstep(stx, fx, gx, sty, fy, gy, stp, f, gd, brackt, stmin, stmax);
+                        dcstep(S.stx, S.fx, S.gx, S.sty, S.fy, S.gy, stp, f, gd, S.brackt, S.stmin, S.stmax);
                     }
-                    if (brackt) {
-                        if (fabs(sty - stx) >= 0.66 * width1) stp = stx + 0.5 * (sty - stx);
-                        width1 = width;
-                        width = fabs(sty - stx);
-                        stmin = py_min2(stx, sty);
-                        stmax = py_max2(stx, sty);
+                    if (S.brackt) {
+                        if (fabs(S.sty - S.stx) >= 0.66 * S.width1) stp = S.stx + 0.5 * (S.sty - S.stx);
+                        S.width1 = S.width;
+                        S.width = fabs(S.sty - S.stx);
+                        S.stmin = py_min2(S.stx, S.sty);
+                        S.stmax = py_max2(S.stx, S.sty);
                     } else {
-                        stmin = stp + 1.1 * (stp - stx);
-                        stmax = stp + 4.0 * (stp - stx);
+                        S.stmin = stp + 1.1 * (stp - S.stx);
+                        S.stmax = stp + 4.0 * (stp - S.stx);
                     }
                     stp = np_clip(stp, stpmin, stpmax);
-                    if ((brackt && (stp <= stmin || stp >= stmax)) ||
-                        (brackt && stmax - stmin <= xtol * stmax))
-                        stp = stx;
-                    w1_it++;
-                    if (!isfinite(stp) || w1_it >= 100) start_w2 = 1;  // WARN / maxiter -> stp None
+                    if ((S.brackt && (stp <= S.stmin || stp >= S.stmax)) ||
+                        (S.brackt && S.stmax - S.stmin <= xtol * S.stmax))
+                        stp = S.stx;
+                    S.w1_it++;
+                    if (!isfinite(stp) || S.w1_it >= 100) start_w2 = 1;  // WARN / maxiter -> stp None
                     else alpha = stp;
                 }
             } else if (ls == LS_W2) {
                 // bracket phase of scalar_search_wolfe2 (scipy/optimize/_linesearch.py:411-466)
                 const double alpha1 = alpha, phi_a1 = f_eval, derphi_a1 = dphi;
-                if (w2_i == 10) {
+                if (S.w2_i == 10) {
                     accept = 1;  // for-else: alpha_star = alpha1, derphi_star None (gradient re-evaluated)
-                } else if (alpha1 == 0.0 || alpha0 > 1e100) {
+                } else if (alpha1 == 0.0 || S.alpha0 > 1e100) {
                     fail = 1;
-                } else if (phi_a1 > old_fval + c1 * alpha1 * derphi0 || (phi_a1 >= phi_a0 && w2_i > 0)) {
-                    start_zoom = 1; zl = alpha0; zh = alpha1; zpl = phi_a0; zph = phi_a1; zdl = derphi_a0;
-                } else if (fabs(derphi_a1) <= -c2 * derphi0) {
+                } else if (phi_a1 > S.old_fval + c1 * alpha1 * S.derphi0 || (phi_a1 >= S.phi_a0 && S.w2_i > 0)) {
+                    start_zoom = 1; zl = S.alpha0; zh = alpha1; zpl = S.phi_a0; zph = phi_a1; zdl = S.derphi_a0;
+                } else if (fabs(derphi_a1) <= -c2 * S.derphi0) {
                     accept = 1;
                 } else if (derphi_a1 >= 0.0) {
-                    start_zoom = 1; zl = alpha1; zh = alpha0; zpl = phi_a1; zph = phi_a0; zdl = derphi_a1;
+                    start_zoom = 1; zl = alpha1; zh = S.alpha0; zpl = phi_a1; zph = S.phi_a0; zdl = derphi_a1;
                 } else {
                     const double alpha2 = py_min2(2.0 * alpha1, 1e100);
-                    alpha0 = alpha1; phi_a0 = phi_a1; derphi_a0 = derphi_a1;
+                    S.alpha0 = alpha1; S.phi_a0 = phi_a1; S.derphi_a0 = derphi_a1;
                     alpha = alpha2;
-                    w2_i++;
+                    S.w2_i++;
                 }
             } else {  // LS_ZOOM — scipy/optimize/_linesearch.py:546-634
                 const double a_j = alpha, phi_aj = f_eval, derphi_aj = dphi;
-                if (phi_aj > old_fval + c1 * a_j * derphi0 || phi_aj >= phi_lo) {
-                    phi_rec = phi_hi; a_rec = a_hi; a_hi = a_j; phi_hi = phi_aj;
+                if (phi_aj > S.old_fval + c1 * a_j * S.derphi0 || phi_aj >= S.phi_lo) {
+                    S.phi_rec = S.phi_hi; S.a_rec = S.a_hi; S.a_hi = a_j; S.phi_hi = phi_aj;
                 } else {
-                    if (fabs(derphi_aj) <= -c2 * derphi0) {
+                    if (fabs(derphi_aj) <= -c2 * S.derphi0) {
                         accept = 1;
                     } else {
-                        if (derphi_aj * (a_hi - a_lo) >= 0.0) {
-                            phi_rec = phi_hi; a_rec = a_hi; a_hi = a_lo; phi_hi = phi_lo;
+                        if (derphi_aj * (S.a_hi - S.a_lo) >= 0.0) {
+                            S.phi_rec = S.phi_hi; S.a_rec = S.a_hi; S.a_hi = S.a_lo; S.phi_hi = S.phi_lo;
                         } else {
-                            phi_rec = phi_lo; a_rec = a_lo;
+                            S.phi_rec = S.phi_lo; S.a_rec = S.a_lo;
                         }
-                        a_lo = a_j; phi_lo = phi_aj; derphi_lo = derphi_aj;
+                        S.a_lo = a_j; S.phi_lo = phi_aj; S.derphi_lo = derphi_aj;
                     }
                 }
                 if (!accept) {
-                    z_i++;
-                    if (z_i > 10) fail = 1;
+                    S.z_i++;
+                    if (S.z_i > 10) fail = 1;
                 }
             }
 
             if (start_w2) {
                 // scalar_search_wolfe2 prologue (scipy/optimize/_linesearch.py:395-409)
                 double alpha1;
-                if (derphi0 != 0.0) alpha1 = py_min2(1.0, ddiv(1.01 * 2 * (old_fval - old_old_fval), derphi0));
+                if (S.derphi0 != 0.0) alpha1 = py_min2(1.0, ddiv(1.01 * 2 * (S.old_fval - S.old_old_fval), S.derphi0));
                 else alpha1 = 1.0;
                 if (alpha1 < 0.0) alpha1 = 1.0;
                 alpha1 = py_min2(alpha1, 1e100);
-                alpha0 = 0.0; phi_a0 = old_fval; derphi_a0 = derphi0; w2_i = 0;
+                S.alpha0 = 0.0; S.phi_a0 = S.old_fval; S.derphi_a0 = S.derphi0; S.w2_i = 0;
                 alpha = alpha1;
                 ls = LS_W2;
             }
             if (start_zoom) {
-                a_lo = zl; a_hi = zh; phi_lo = zpl; phi_hi = zph; derphi_lo = zdl;
-                phi_rec = old_fval; a_rec = 0.0; z_i = 0;
+                S.a_lo = zl; S.a_hi = zh; S.phi_lo = zpl; S.phi_hi = zph; S.derphi_lo = zdl;
+                S.phi_rec = S.old_fval; S.a_rec = 0.0; S.z_i = 0;
                 ls = LS_ZOOM;
             }
             if (ls == LS_ZOOM && !accept && !fail) {
                 // next trial step of _zoom
-                const double dalpha = a_hi - a_lo;
+                const double dalpha = S.a_hi - S.a_lo;
                 double za, zb;
-                if (dalpha < 0.0) { za = a_hi; zb = a_lo; } else { za = a_lo; zb = a_hi; }
+                if (dalpha < 0.0) { za = S.a_hi; zb = S.a_lo; } else { za = S.a_lo; zb = S.a_hi; }
                 double a_j = nan("");
                 double cchk = 0.0;
-                if (z_i > 0) {
+                if (S.z_i > 0) {
                     cchk = 0.2 * dalpha;
-                    a_j = cubicmin(a_lo, phi_lo, derphi_lo, a_hi, phi_hi, a_rec, phi_rec);
+                    a_j = cubicmin(S.a_lo, S.phi_lo, S.derphi_lo, S.a_hi, S.phi_hi, S.a_rec, S.phi_rec);
                 }
-                if (z_i == 0 || isnan(a_j) || a_j > zb - cchk || a_j < za + cchk) {
+                if (S.z_i == 0 || isnan(a_j) || a_j > zb - cchk || a_j < za + cchk) {
                     const double qchk = 0.1 * dalpha;
-                    a_j = quadmin(a_lo, phi_lo, derphi_lo, a_hi, phi_hi);
-                    if (isnan(a_j) || a_j > zb - qchk || a_j < za + qchk) a_j = a_lo + 0.5 * dalpha;
+                    a_j = quadmin(S.a_lo, S.phi_lo, S.derphi_lo, S.a_hi, S.phi_hi);
+                    if (isnan(a_j) || a_j > zb - qchk || a_j < za + qchk) a_j = S.a_lo + 0.5 * dalpha;
                 }
                 alpha = a_j;
             }
@@ -890,14 +893,14 @@ __global__ void __launch_bounds__(256, 1) estep_kernel(const EstepParams P) {
                     gm = nanmax(gm, fabs(g[i]));
                     pm = nanmax(pm, fabs(p[i]));
                 }
-                old_old_fval = old_fval;
-                old_fval = f_eval;
+                S.old_old_fval = S.old_fval;
+                S.old_fval = f_eval;
                 k_it++;
-                gnorm = warp_max(gm);
+                S.gnorm = warp_max(gm);
                 pm = warp_max(pm);
-                if (gnorm <= 1e-5) { done = 1; }
+                if (S.gnorm <= 1e-5) { done = 1; }
                 else if (alpha_k * pm <= 0.0) { done = 1; }
-                else if (!isfinite(old_fval)) { warnflag = 2; done = 1; }
+                else if (!isfinite(S.old_fval)) { warnflag = 2; done = 1; }
                 else {
                     const double rhok_inv = warp_sum(ys_l);
                     const double rho = (rhok_inv == 0.0) ? 1000.0 : ddiv(1.0, rhok_inv);
@@ -959,7 +962,7 @@ __global__ void __launch_bounds__(256, 1) estep_kernel(const EstepParams P) {
             }
 
             if (new_iter && !done) {
-                if (!(gnorm > 1e-5) || !(k_it < maxiter)) {
+                if (!(S.gnorm > 1e-5) || !(k_it < maxiter)) {
                     done = 1;
                 } else {
                     if (new_iter == 1) {
@@ -969,29 +972,29 @@ __global__ void __launch_bounds__(256, 1) estep_kernel(const EstepParams P) {
                     double d_l = 0.0;
 #pragma unroll
                     for (int i = 0; i < KPL; ++i) d_l += g[i] * p[i];
-                    derphi0 = warp_sum(d_l);
+                    S.derphi0 = warp_sum(d_l);
                     // scalar_search_wolfe1 prologue + DCSRCH START
                     double alpha1;
-                    if (derphi0 != 0.0) {
-                        alpha1 = py_min2(1.0, ddiv(1.01 * 2 * (old_fval - old_old_fval), derphi0));
+                    if (S.derphi0 != 0.0) {
+                        alpha1 = py_min2(1.0, ddiv(1.01 * 2 * (S.old_fval - S.old_old_fval), S.derphi0));
                         if (alpha1 < 0.0) alpha1 = 1.0;
                     } else alpha1 = 1.0;
-                    if (alpha1 < stpmin || alpha1 > stpmax || derphi0 >= 0.0 || !isfinite(alpha1)) {
+                    if (alpha1 < stpmin || alpha1 > stpmax || S.derphi0 >= 0.0 || !isfinite(alpha1)) {
                         // task = ERROR -> stp None -> wolfe2
                         double a1;
-                        if (derphi0 != 0.0) a1 = py_min2(1.0, ddiv(1.01 * 2 * (old_fval - old_old_fval), derphi0));
+                        if (S.derphi0 != 0.0) a1 = py_min2(1.0, ddiv(1.01 * 2 * (S.old_fval - S.old_old_fval), S.derphi0));
                         else a1 = 1.0;
                         if (a1 < 0.0) a1 = 1.0;
                         a1 = py_min2(a1, 1e100);
-                        alpha0 = 0.0; phi_a0 = old_fval; derphi_a0 = derphi0; w2_i = 0;
+                        S.alpha0 = 0.0; S.phi_a0 = S.old_fval; S.derphi_a0 = S.derphi0; S.w2_i = 0;
                         alpha = a1;
                         ls = LS_W2;
                     } else {
-                        brackt = 0; stage = 1; finit = old_fval; ginit = derphi0; gtest = c1 * ginit;
-                        width = stpmax - stpmin; width1 = width * 2.0;
-                        stx = 0.0; fx = finit; gx = ginit; sty = 0.0; fy = finit; gy = ginit;
-                        stmin = 0.0; stmax = alpha1 + 4.0 * alpha1;
-                        w1_it = 1;  // the START call was iteration 0 of DCSRCH.__call__
+                        S.brackt = 0; S.stage = 1; S.finit = S.old_fval; S.ginit = S.derphi0; S.gtest = c1 * S.ginit;
+                        S.width = stpmax - stpmin; S.width1 = S.width * 2.0;
+                        S.stx = 0.0; S.fx = S.finit; S.gx = S.ginit; S.sty = 0.0; S.fy = S.finit; S.gy = S.ginit;
+                        S.stmin = 0.0; S.stmax = alpha1 + 4.0 * alpha1;
+                        S.w1_it = 1;  // the START call was iteration 0 of DCSRCH.__call__
                         alpha = alpha1;
                         ls = LS_W1;
                     }
@@ -1007,13 +1010,126 @@ __global__ void __launch_bounds__(256, 1) estep_kernel(const EstepParams P) {
         if (status != 2) {
             if (k_it >= maxiter) status = 1;
             else {
-                bool bad = isnan(gnorm) || isnan(old_fval);
+                bool bad = isnan(S.gnorm) || isnan(S.old_fval);
 #pragma unroll
                 for (int i = 0; i < KPL; ++i) bad = bad || isnan(x[i]);
                 status = __any_sync(STM_FULL, bad) ? 3 : 0;
             }
         }
+#pragma unroll
+        for (int i = 0; i < KPL; ++i) {
+            const int k = lane + 32 * i;
+            if (k < K1) P.eta[(size_t)d * K1 + k] = x[i];
+        }
+        if (lane == 0) {
+            const int nit_c = k_it > 0xfffff ? 0xfffff : k_it;
+            P.doc_info[d] = status | (nit_c << 4);
+            P.doc_nfev[d] = nfev;
+        }
+        __syncwarp();
+#if STM_DBG_TIMING
+        { const long long t_p4 = clock64(); dbg_t[4] += t_p4 - t_post0; }   // slot 4: status + stores
+#endif
+    }  // document loop
+#if STM_DBG_TIMING
+    if (lane == 0)
+        for (int i = 0; i < 16; ++i) atomicAdd(P.dbg_cycles + i, (unsigned long long)dbg_t[i]);
+#endif
+}
 
+// ===== POST KERNEL =====
+// Kernel B: everything after the optimiser for one document (stm.py:546-590): theta, phi -> beta_ss,
+// Hessian, make_pd / Cholesky, bound, nu -> sigma_ss.  Reads the eta kernel A wrote; ORs the repair
+// stage into doc_info.
+template <int KPL>
+__global__ void __launch_bounds__(256, 1) post_kernel(const EstepParams P) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    const int K = P.K, K1 = K - 1, TS = P.TS;
+    constexpr int KV = KPL * 32;
+    constexpr int KVS = KV + 8;  // padded stride of the shared K-vectors (TS <= KV+4, block reads <= KV+6)
+    const int HS = K1 | 1;  // odd row stride (doubles) of the dense (K-1)x(K-1) matrices in smem
+
+    // ---- per-warp shared memory carve-up (post_smem_per_warp in stm_b200.cu mirrors this) -----
+    unsigned char* base = smem_raw + (size_t)warp * P.smem_per_warp;
+    size_t tile_bytes = (size_t)P.n_cap * TS * 4;
+    const size_t h_bytes = (size_t)K1 * HS * 8;
+    if (h_bytes > tile_bytes) tile_bytes = h_bytes;
+    tile_bytes = (tile_bytes + 127) & ~(size_t)127;
+    float* tile = reinterpret_cast<float*>(base);
+    double* Hm = reinterpret_cast<double*>(base);  // aliases the tile once it is dead
+    double* wv = reinterpret_cast<double*>(base + tile_bytes);            // [n_cap] per-word fp64
+    double* wv2 = wv + P.n_cap;                                           // [n_cap] sqrt(c_v)
+    double* vec = wv2 + P.n_cap;                                          // [4][KVS]
+    float* cw = reinterpret_cast<float*>(vec + 4 * KVS);                  // [n_cap] counts
+    int* wid = reinterpret_cast<int*>(cw + P.n_cap);                      // [n_cap]
+    uint64_t* mbar = reinterpret_cast<uint64_t*>(wid + ((P.n_cap + 1) & ~1));
+    double* v0 = vec;            // e / broadcast scratch
+    double* v1 = vec + KVS;
+    double* v2 = vec + 2 * KVS;
+    double* v3 = vec + 3 * KVS;
+    for (int i = lane; i < 4 * KVS; i += 32) vec[i] = 0.0;  // pads stay zero for the whole kernel
+
+    if (lane == 0) mbar_init(mbar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    __syncwarp();
+    uint32_t parity = 0;
+#if STM_DBG_TIMING
+    long long dbg_t[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+#endif
+
+    const int gwarp = blockIdx.x * (blockDim.x >> 5) + warp;
+    double* Hg = P.scratch + (size_t)gwarp * P.scratch_stride + (size_t)K1 * K1;  // Laplace Hessian bounce [K1][K1]
+    double* sig_acc = P.sigma_ss_rep + (size_t)(gwarp % P.n_rep) * K1 * K1;
+
+    // diagonal of siginv, lane-distributed
+    double Sd[KPL];
+#pragma unroll
+    for (int i = 0; i < KPL; ++i) {
+        const int k = lane + 32 * i;
+        Sd[i] = (k < K1) ? P.prior[k] : 0.0;
+    }
+    const double sigmaentropy = P.prior[K1];
+
+    for (;;) {
+        int qi = 0;
+        if (lane == 0) qi = (int)atomicAdd(P.queue, 1u);
+        qi = __shfl_sync(STM_FULL, qi, 0);
+        if (qi >= P.n_docs) break;
+        STM_T(t_post0);
+        const int d = P.docs[qi];
+        const long long p0 = P.doc_ptr[d];
+        const int n = (int)(P.doc_ptr[d + 1] - p0);
+        const int asp = P.aspect ? P.aspect[d] : 0;
+        const float* beta_a = P.beta_t + (size_t)asp * P.V * TS;
+
+        // ---- stage ids / counts, then TMA-gather the beta rows --------------------------------
+        fence_proxy_async();  // previous document's generic writes to this smem precede async writes
+        __syncwarp();
+        if (lane == 0) mbar_expect_tx(mbar, (uint32_t)(n * TS * 4));
+        __syncwarp();
+        double nsum_l = 0.0;
+        for (int v = lane; v < n; v += 32) {
+            const int w = P.word_id[p0 + v];
+            const float c = P.count[p0 + v];
+            wid[v] = w;
+            cw[v] = c;
+            nsum_l += (double)c;
+            tma_row_g2s(tile + (size_t)v * TS, beta_a + (size_t)w * TS, (uint32_t)(TS * 4), mbar);
+        }
+        const double Nsum = warp_sum(nsum_l);           // np.sum(word_count)       stm.py:955
+
+        double x[KPL], mu[KPL];
+#pragma unroll
+        for (int i = 0; i < KPL; ++i) {
+            const int k = lane + 32 * i;
+            x[i] = (k < K1) ? P.eta[(size_t)d * K1 + k] : 0.0;
+            mu[i] = (k < K1) ? P.mu[(size_t)d * K1 + k] : 0.0;
+        }
+        mbar_wait(mbar, parity);
+        parity ^= 1;
+        __syncwarp();
         // =======================================================================================
         // post-optimisation: theta, phi -> beta_ss, Hessian, Cholesky, bound, nu -> sigma_ss
         // =======================================================================================
@@ -1039,14 +1155,13 @@ __global__ void __launch_bounds__(256, 1) estep_kernel(const EstepParams P) {
             for (int i = 0; i < KPL; ++i) {
                 const int k = lane + 32 * i;
                 th[i] = th[i] / ss;
-                if (k < K1) P.eta[(size_t)d * K1 + k] = x[i];
                 if (k < K) P.theta[(size_t)d * K + k] = eu[i] / se;  // stm.py:547-549 (no max shift)
                 v0[k] = (k < K) ? eu[i] : 0.0;
                 v1[k] = (k < K) ? th[i] * eu[i] : 0.0;
             }
             __syncwarp();
         }
-        if (STM_DBG_SKIP_POST) { if (lane == 0) { P.doc_bound[d] = 0.0; P.doc_info[d] = status; P.doc_nfev[d] = nfev; } continue; }
+        if (STM_DBG_SKIP_POST) { if (lane == 0) P.doc_bound[d] = 0.0; continue; }
         // colsum_v = sum_k e_k beta_kv and the log-likelihood part of the bound (stm.py:1088-1096)
         STM_T(t_p1);
         STM_TACC(4, t_post0, t_p1);         // slot 4: status, theta
@@ -1205,7 +1320,7 @@ __global__ void __launch_bounds__(256, 1) estep_kernel(const EstepParams P) {
         // PD test + repairs (stm.py:1017-1021, 1039-1048).  "all eigenvalues > 0" is restated as
         // "Cholesky succeeds".  The factor overwrites the strict lower triangle + a separate diagonal
         // so the matrix can be restored from its upper triangle for the retries.
-        if (STM_DBG_SKIP_DENSE) { if (lane == 0) { P.doc_bound[d] = 0.0; P.doc_info[d] = status; P.doc_nfev[d] = nfev; } continue; }
+        if (STM_DBG_SKIP_DENSE) { if (lane == 0) P.doc_bound[d] = 0.0; continue; }
         STM_T(t_p2);
         STM_TACC(5, t_p1, t_p2);            // slot 5: colsum + Hessian (DMMA) + assemble
         int repair = 0;
@@ -1259,9 +1374,7 @@ __global__ void __launch_bounds__(256, 1) estep_kernel(const EstepParams P) {
         const double bound = loglik - warp_sum(det_l) - 0.5 * warp_sum(q_l) - sigmaentropy;
         if (lane == 0) {
             P.doc_bound[d] = bound;
-            const int nit_c = k_it > 0xfffff ? 0xfffff : k_it;
-            P.doc_info[d] = status | (nit_c << 4) | (repair << 24);
-            P.doc_nfev[d] = nfev;
+            P.doc_info[d] = (P.doc_info[d] & 0xffffff) | (repair << 24);
         }
 
         // nu = H^-1 = L^-T L^-1 (stm.py:1052-1066), accumulated into sigma_ss (stm.py:582)

@@ -24,9 +24,9 @@ struct LengthClass {
     int J = 0;           // words per lane per pass (template parameter)
     int n_docs = 0;
     int* d_docs = nullptr;
-    int warps = 0;       // warps per CTA
-    int smem_per_warp = 0;
-    int grid = 0;
+    // kernel A (BFGS) / kernel B (post-optimisation): warps per CTA, bytes of shared memory per warp, CTAs
+    int warps = 0, smem_per_warp = 0, grid = 0;
+    int post_warps = 0, post_smem_per_warp = 0, post_grid = 0;
 };
 
 }  // namespace
@@ -103,33 +103,55 @@ int beta_stride(int K) {
     return ts;
 }
 
-size_t smem_per_warp_bytes(int n_cap, int TS, int K1, int KPL) {
+// mirrors the carve-up at the top of stm::bfgs_kernel
+size_t bfgs_smem_per_warp(int n_cap, int TS, int KPL) {
+    const size_t tile = ((size_t)n_cap * TS * 4 + 127) & ~(size_t)127;
+    const int KVS = KPL * 32 + 8;
+    const size_t total = tile + (size_t)n_cap * 8 + (size_t)4 * KVS * 8 + sizeof(stm::LsState) +
+                         (size_t)((n_cap + 1) & ~1) * 4 + 8;
+    return (total + 127) & ~(size_t)127;
+}
+// mirrors the carve-up at the top of stm::post_kernel
+size_t post_smem_per_warp(int n_cap, int TS, int K1, int KPL) {
     const int HS = K1 | 1;
     size_t tile = (size_t)n_cap * TS * 4;
     const size_t hb = (size_t)K1 * HS * 8;
     if (hb > tile) tile = hb;
     tile = (tile + 127) & ~(size_t)127;
     const int KVS = KPL * 32 + 8;
-    size_t total = tile + (size_t)n_cap * 16 + (size_t)4 * KVS * 8 + (size_t)n_cap * 4 + (size_t)n_cap * 4 + 8;
+    const size_t total = tile + (size_t)n_cap * 16 + (size_t)4 * KVS * 8 + (size_t)n_cap * 4 +
+                         (size_t)((n_cap + 1) & ~1) * 4 + 8;
     return (total + 127) & ~(size_t)127;
 }
 
 }  // namespace
 // one translation unit per KPL (estep_inst.cu compiled with -DSTM_KPL=n) so the 16 kernel
 // instantiations build in parallel
-cudaError_t stm_launch_kpl1(const stm::EstepParams&, int, int, int, size_t, cudaStream_t);
-cudaError_t stm_launch_kpl2(const stm::EstepParams&, int, int, int, size_t, cudaStream_t);
-cudaError_t stm_launch_kpl3(const stm::EstepParams&, int, int, int, size_t, cudaStream_t);
-cudaError_t stm_launch_kpl4(const stm::EstepParams&, int, int, int, size_t, cudaStream_t);
+cudaError_t stm_launch_bfgs_kpl1(const stm::EstepParams&, int, int, int, size_t, cudaStream_t);
+cudaError_t stm_launch_bfgs_kpl2(const stm::EstepParams&, int, int, int, size_t, cudaStream_t);
+cudaError_t stm_launch_bfgs_kpl3(const stm::EstepParams&, int, int, int, size_t, cudaStream_t);
+cudaError_t stm_launch_bfgs_kpl4(const stm::EstepParams&, int, int, int, size_t, cudaStream_t);
+cudaError_t stm_launch_post_kpl1(const stm::EstepParams&, int, int, size_t, cudaStream_t);
+cudaError_t stm_launch_post_kpl2(const stm::EstepParams&, int, int, size_t, cudaStream_t);
+cudaError_t stm_launch_post_kpl3(const stm::EstepParams&, int, int, size_t, cudaStream_t);
+cudaError_t stm_launch_post_kpl4(const stm::EstepParams&, int, int, size_t, cudaStream_t);
 namespace {
 
-cudaError_t launch_class(int KPL, const stm::EstepParams& P, int J, int grid, int block, size_t smem,
-                         cudaStream_t st) {
+cudaError_t launch_bfgs(int KPL, const stm::EstepParams& P, int J, int grid, int block, size_t smem,
+                        cudaStream_t st) {
     switch (KPL) {
-        case 1: return stm_launch_kpl1(P, J, grid, block, smem, st);
-        case 2: return stm_launch_kpl2(P, J, grid, block, smem, st);
-        case 3: return stm_launch_kpl3(P, J, grid, block, smem, st);
-        default: return stm_launch_kpl4(P, J, grid, block, smem, st);
+        case 1: return stm_launch_bfgs_kpl1(P, J, grid, block, smem, st);
+        case 2: return stm_launch_bfgs_kpl2(P, J, grid, block, smem, st);
+        case 3: return stm_launch_bfgs_kpl3(P, J, grid, block, smem, st);
+        default: return stm_launch_bfgs_kpl4(P, J, grid, block, smem, st);
+    }
+}
+cudaError_t launch_post(int KPL, const stm::EstepParams& P, int grid, int block, size_t smem, cudaStream_t st) {
+    switch (KPL) {
+        case 1: return stm_launch_post_kpl1(P, grid, block, smem, st);
+        case 2: return stm_launch_post_kpl2(P, grid, block, smem, st);
+        case 3: return stm_launch_post_kpl3(P, grid, block, smem, st);
+        default: return stm_launch_post_kpl4(P, grid, block, smem, st);
     }
 }
 
@@ -505,17 +527,21 @@ int stm_set_corpus(stm_ctx* ctx, int64_t D, const int64_t* doc_ptr, const int32_
         std::stable_sort(members[ci].begin(), members[ci].end(), [&](int a, int b) {
             return (doc_ptr[a + 1] - doc_ptr[a]) > (doc_ptr[b + 1] - doc_ptr[b]);
         });
-        lc.smem_per_warp = (int)smem_per_warp_bytes(lc.n_cap, ctx->TS, ctx->K1, ctx->KPL);
-        lc.warps = std::min(8, ctx->max_smem / lc.smem_per_warp);
+        lc.smem_per_warp = (int)bfgs_smem_per_warp(lc.n_cap, ctx->TS, ctx->KPL);
+        lc.warps = std::min(STM_BFGS_MAX_THREADS / 32, ctx->max_smem / lc.smem_per_warp);
+        lc.post_smem_per_warp = (int)post_smem_per_warp(lc.n_cap, ctx->TS, ctx->K1, ctx->KPL);
+        lc.post_warps = std::min(8, ctx->max_smem / lc.post_smem_per_warp);
         if (const char* cap = getenv("STM_MAX_WARPS")) {  // development knob (occupancy experiments)
             const int c = atoi(cap);
-            if (c >= 1) lc.warps = std::min(lc.warps, c);
+            if (c >= 1) { lc.warps = std::min(lc.warps, c); lc.post_warps = std::min(lc.post_warps, c); }
         }
-        if (lc.warps < 1)
+        if (lc.warps < 1 || lc.post_warps < 1)
             return fail(ctx, STM_ERR_UNSUPPORTED,
-                        "a document's beta tile (" + std::to_string(lc.smem_per_warp) +
+                        "a document's beta tile (" + std::to_string(lc.post_smem_per_warp) +
                             " bytes) does not fit in shared memory");
         lc.grid = std::min(ctx->sm_count, (lc.n_docs + lc.warps - 1) / lc.warps);
+        lc.post_grid = std::min(ctx->sm_count, (lc.n_docs + lc.post_warps - 1) / lc.post_warps);
+        max_warps = std::max(max_warps, lc.post_grid * lc.post_warps);
         CU(cudaMalloc(&lc.d_docs, sizeof(int) * lc.n_docs));
         CU(cudaMemcpy(lc.d_docs, members[ci].data(), sizeof(int) * lc.n_docs, cudaMemcpyHostToDevice));
         max_warps = std::max(max_warps, lc.grid * lc.warps);
@@ -533,7 +559,7 @@ int stm_set_corpus(stm_ctx* ctx, int64_t D, const int64_t* doc_ptr, const int32_
         CU(cudaMalloc(&ctx->d_aspect, sizeof(int) * std::max<int64_t>(D, 1)));
         CU(cudaMemcpy(ctx->d_aspect, aspect, sizeof(int) * D, cudaMemcpyHostToDevice));
     }
-    CU(cudaMalloc(&ctx->d_queues, sizeof(unsigned int) * 16));
+    CU(cudaMalloc(&ctx->d_queues, sizeof(unsigned int) * 32));
     CU(cudaMalloc(&ctx->d_dbg, sizeof(unsigned long long) * 16));
     CU(cudaMemset(ctx->d_dbg, 0, sizeof(unsigned long long) * 16));
     ctx->max_warps_total = std::max(max_warps, 1);
@@ -594,7 +620,7 @@ int stm_estep(stm_ctx* ctx, const float* beta_t_dev, const double* mu_dev, const
     const int K1 = ctx->K1;
     CU(cudaMemsetAsync(stats_dev + off[0], 0, sizeof(double) * (size_t)ctx->A * ctx->V * ctx->TS, st));
     CU(cudaMemsetAsync(ctx->d_sigma_rep, 0, sizeof(double) * ctx->n_rep * K1 * K1, st));
-    CU(cudaMemsetAsync(ctx->d_queues, 0, sizeof(unsigned int) * 16, st));
+    CU(cudaMemsetAsync(ctx->d_queues, 0, sizeof(unsigned int) * 32, st));
     int ci = 0;
     for (const auto& lc : ctx->classes) {
         stm::EstepParams P;
@@ -609,9 +635,14 @@ int stm_estep(stm_ctx* ctx, const float* beta_t_dev, const double* mu_dev, const
         P.scratch = ctx->d_scratch; P.scratch_stride = ctx->scratch_stride;
         P.n_cap = lc.n_cap; P.smem_per_warp = lc.smem_per_warp;
         P.dbg_cycles = ctx->d_dbg;
-        const size_t smem = (size_t)lc.smem_per_warp * lc.warps;
-        CU(launch_class(ctx->KPL, P, lc.J, lc.grid, lc.warps * 32, smem, st));
-        ctx->launches++;
+        static const int dev_skip = getenv("STM_DEV_SKIP") ? atoi(getenv("STM_DEV_SKIP")) : 0;  // 1: no kernel A, 2: no kernel B (timing only)
+        if (dev_skip != 1)
+            CU(launch_bfgs(ctx->KPL, P, lc.J, lc.grid, lc.warps * 32, (size_t)lc.smem_per_warp * lc.warps, st));
+        P.queue = ctx->d_queues + 16 + ci;
+        P.smem_per_warp = lc.post_smem_per_warp;
+        if (dev_skip != 2)
+            CU(launch_post(ctx->KPL, P, lc.post_grid, lc.post_warps * 32, (size_t)lc.post_smem_per_warp * lc.post_warps, st));
+        ctx->launches += 2;
         ci++;
     }
     estep_epilogue_kernel<<<1, 1024, 0, st>>>(ctx->d_sigma_rep, ctx->n_rep, K1, doc_bound_dev, ctx->D,
