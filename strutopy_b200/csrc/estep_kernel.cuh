@@ -53,7 +53,7 @@
 #define STM_DBG_SKIP_DENSE 0
 #endif
 #ifndef STM_BFGS_MAX_THREADS
-#define STM_BFGS_MAX_THREADS 256   // launch bound of kernel A (register budget = 65536 / this)
+#define STM_BFGS_MAX_THREADS 448   // launch bound of kernel A (register budget = 65536 / this)
 #endif
 #define STM_PRAGMA2_(x) _Pragma(#x)
 #define STM_PRAGMA_(x) STM_PRAGMA2_(x)
@@ -101,7 +101,10 @@ struct EstepParams {
     long long scratch_stride;   // doubles per warp
     // shared memory geometry
     int n_cap;                  // tile rows (words) per warp
-    int smem_per_warp;          // bytes
+    int smem_per_warp;          // bytes of the per-warp tile block (kernel A: smem warps only)
+    int smem_small;             // kernel A: bytes of the per-warp small block (K-vectors, line-search state)
+    int tm_warps;               // kernel A: warps 0..tm_warps-1 keep their tile in TMEM (0, 4 or 8)
+    int tm_cols;                // kernel A: TMEM columns per TMEM warp (512 or 256)
     unsigned long long* dbg_cycles;  // [8] phase cycle counters (only written when STM_DBG_TIMING)
 };
 #if STM_DBG_TIMING
@@ -299,21 +302,23 @@ static __device__ STM_NOINLINE double log_noinline(double x) { return log(x); }
 static __device__ STM_NOINLINE double exp_noinline(double x) { return exp(x); }
 
 // sum_v c_v log(s_v) accumulated as a PRODUCT: s = m2 * 2^e (m2 in [1,2)), prod *= m2^c, esum += c*e.
-// One log per lane per evaluation instead of one per word.  Falls back to c*log(s) for
-// non-integer / large counts and for zero, subnormal, negative or non-finite s.
+// One log per lane per evaluation instead of one per word.  The inlined fast path handles c = 1 and a
+// positive normal s (almost every word); everything else (c = 2..8, non-integer / large counts, zero,
+// subnormal, negative or non-finite s) goes through ONE out-of-line copy (instruction footprint).
 struct LogProd {
     double prod;   // running mantissa product, kept in [1, 2^64)
-    double esum;   // running exponent sum (exact small integers)
+    int esum;      // running exponent sum
     double extra;  // fallback terms c*log(s)
 };
-__device__ __forceinline__ void logprod_init(LogProd& a) { a.prod = 1.0; a.esum = 0.0; a.extra = 0.0; }
+struct LogProdTerm { double pw; double extra; int e; };
+__device__ __forceinline__ void logprod_init(LogProd& a) { a.prod = 1.0; a.esum = 0; a.extra = 0.0; }
 __device__ __forceinline__ void logprod_renorm(LogProd& a) {
     const int hi = __double2hiint(a.prod);
-    const int e = ((hi >> 20) & 0x7ff) - 1023;
-    a.esum += (double)e;
+    a.esum += ((hi >> 20) & 0x7ff) - 1023;
     a.prod = __hiloint2double((hi & 0x800fffff) | 0x3ff00000, __double2loint(a.prod));
 }
-__device__ __forceinline__ void logprod_add(LogProd& a, double s, float cf) {
+static __device__ __noinline__ LogProdTerm logprod_slow(double s, float cf) {
+    LogProdTerm t;
     const int hi = __double2hiint(s);
     const int be = (hi >> 20) & 0x7ff;           // biased exponent; sign bit excluded below
     const int ci = (int)cf;
@@ -326,14 +331,25 @@ __device__ __forceinline__ void logprod_add(LogProd& a, double s, float cf) {
         if (ci & 2) pw *= q2;
         if (ci & 4) pw *= q4;
         if (ci & 8) pw *= q4 * q4;
-        a.prod *= pw;
-        a.esum += (double)(ci * (be - 1023));
+        t.pw = pw; t.e = ci * (be - 1023); t.extra = 0.0;
     } else {
-        a.extra += (double)cf * log_noinline(s);
+        t.pw = 1.0; t.e = 0; t.extra = (double)cf * log_noinline(s);
+    }
+    return t;
+}
+__device__ __forceinline__ void logprod_add(LogProd& a, double s, float cf) {
+    const int hi = __double2hiint(s);
+    const unsigned se = (unsigned)hi >> 20;      // sign | biased exponent: positive normal iff 1 <= se <= 0x7fe
+    if (cf == 1.0f && (se - 1u) < 0x7feu) {
+        a.prod *= __hiloint2double((hi & 0x000fffff) | 0x3ff00000, __double2loint(s));
+        a.esum += (int)se - 1023;
+    } else {
+        const LogProdTerm t = logprod_slow(s, cf);
+        a.prod *= t.pw; a.esum += t.e; a.extra += t.extra;
     }
 }
 __device__ __forceinline__ double logprod_value(const LogProd& a) {
-    return a.esum * 0.6931471805599453 + log_noinline(a.prod) + a.extra;
+    return (double)a.esum * 0.6931471805599453 + log_noinline(a.prod) + a.extra;
 }
 
 // ---- TMA bulk copy + mbarrier (PTX) -----------------------------------------------------------
@@ -372,6 +388,46 @@ __device__ __forceinline__ void fence_proxy_async() {
 __device__ __forceinline__ void red_add_f64(double* addr, double v) {
     asm volatile("red.global.add.f64 [%0], %1;" ::"l"(addr), "d"(v) : "memory");
 }
+
+// ---- tensor memory (TMEM) as tile storage: tcgen05.st / tcgen05.ld, shape 32x32b (thread l of the
+// warp <-> TMEM lane 32*(warp%4)+l, registers <-> consecutive columns) ----------------------------
+__device__ __forceinline__ void tm_st8(uint32_t taddr, const float4& a, const float4& b) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"r"(taddr),
+                 "r"(__float_as_uint(a.x)), "r"(__float_as_uint(a.y)), "r"(__float_as_uint(a.z)),
+                 "r"(__float_as_uint(a.w)), "r"(__float_as_uint(b.x)), "r"(__float_as_uint(b.y)),
+                 "r"(__float_as_uint(b.z)), "r"(__float_as_uint(b.w))
+                 : "memory");
+}
+__device__ __forceinline__ void tm_st4(uint32_t taddr, const float4& a) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1,%2,%3,%4};" ::"r"(taddr),
+                 "r"(__float_as_uint(a.x)), "r"(__float_as_uint(a.y)), "r"(__float_as_uint(a.z)),
+                 "r"(__float_as_uint(a.w))
+                 : "memory");
+}
+__device__ __forceinline__ void tm_st2(uint32_t taddr, const float2& a) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x2.b32 [%0], {%1,%2};" ::"r"(taddr), "r"(__float_as_uint(a.x)),
+                 "r"(__float_as_uint(a.y))
+                 : "memory");
+}
+__device__ __forceinline__ void tm_ld8(uint32_t taddr, uint32_t (&v)[8]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+                 : "r"(taddr)
+                 : "memory");
+}
+__device__ __forceinline__ void tm_ld4(uint32_t taddr, uint32_t (&v)[4]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3])
+                 : "r"(taddr)
+                 : "memory");
+}
+__device__ __forceinline__ void tm_ld2(uint32_t taddr, uint32_t (&v)[2]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x2.b32 {%0,%1}, [%2];" : "=r"(v[0]), "=r"(v[1]) : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tm_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tm_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+// beta_f2d on raw bits (what tcgen05.ld returns)
+__device__ __forceinline__ double beta_u2d(uint32_t u) { return beta_f2d(__uint_as_float(u)); }
 
 // ---- dense (K-1)x(K-1) helpers on a shared-memory matrix, one warp, out of line -------------------
 // Storage convention: Hm is [K1][HS] (HS odd).  The UPPER triangle keeps the original symmetric
@@ -482,25 +538,49 @@ __global__ void __launch_bounds__(STM_BFGS_MAX_THREADS, 1) bfgs_kernel(const Est
     constexpr int KV = KPL * 32;
     constexpr int KVS = KV + 8;  // padded stride of the shared K-vectors (TS <= KV+4, block reads <= KV+6)
 
-    // ---- per-warp shared memory carve-up (bfgs_smem_per_warp in stm_b200.cu mirrors this) -----
-    unsigned char* base = smem_raw + (size_t)warp * P.smem_per_warp;
-    const size_t tile_bytes = ((size_t)P.n_cap * TS * 4 + 127) & ~(size_t)127;
-    float* tile = reinterpret_cast<float*>(base);
-    double* wv = reinterpret_cast<double*>(base + tile_bytes);            // [n_cap] c_v / colsum_v (a_k precompute)
-    double* vec = wv + P.n_cap;                                           // [4][KVS]
+    // ---- shared memory carve-up (bfgs_smem_* in stm_b200.cu mirror this) -----------------------
+    // [small block x nwarps][tile block x (nwarps - tm_warps)].  Warps < tm_warps keep their beta
+    // tile in TENSOR MEMORY (tcgen05.st / tcgen05.ld, lane <-> word, columns <-> topics): TMEM is
+    // 256 KB of otherwise idle on-chip storage, which more than doubles the documents in flight per SM.
+    const int nwarps = blockDim.x >> 5;
+    const bool is_tm = warp < P.tm_warps;
+    unsigned char* small = smem_raw + (size_t)warp * P.smem_small;
+    double* vec = reinterpret_cast<double*>(small);                       // [4][KVS]
     LsState& S = *reinterpret_cast<LsState*>(vec + 4 * KVS);
-    float* cw = reinterpret_cast<float*>(vec + 4 * KVS + sizeof(LsState) / 8);  // [n_cap] counts
-    uint64_t* mbar = reinterpret_cast<uint64_t*>(cw + ((P.n_cap + 1) & ~1));
+    uint64_t* mbar = reinterpret_cast<uint64_t*>(small + 4 * KVS * 8 + sizeof(LsState));
+    unsigned char* tbase = smem_raw + (size_t)nwarps * P.smem_small +
+                           (size_t)(is_tm ? 0 : warp - P.tm_warps) * P.smem_per_warp;
+    const size_t tile_bytes = ((size_t)P.n_cap * TS * 4 + 127) & ~(size_t)127;
+    float* tile = reinterpret_cast<float*>(tbase);                        // smem warps only
+    float* cw = reinterpret_cast<float*>(tbase + tile_bytes);             // [n_cap] counts
     double* v0 = vec;            // e / broadcast scratch
     double* v1 = vec + KVS;
     double* v2 = vec + 2 * KVS;
     double* v3 = vec + 3 * KVS;
+    // c_v / colsum_v of the a_k precompute: borrows v1..v3 when it fits, else its own block
+    double* wv = (P.n_cap <= 3 * KVS) ? v1 : reinterpret_cast<double*>(cw + ((P.n_cap + 1) & ~1));
     for (int i = lane; i < 4 * KVS; i += 32) vec[i] = 0.0;  // pads stay zero for the whole kernel
 
     if (lane == 0) mbar_init(mbar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     __syncwarp();
     uint32_t parity = 0;
+    // TMEM: one allocation of all 512 columns per CTA (1 CTA per SM); warp w owns lanes
+    // 32*(w&3)..+31 (the only lanes it can address) and columns (w>>2)*tm_cols..+tm_cols-1.
+    __shared__ uint32_t tm_base_s;
+    if (P.tm_warps > 0) {
+        if (warp == 0) {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(
+                smem_u32(&tm_base_s)));
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;");
+        __syncthreads();
+        asm volatile("tcgen05.fence::after_thread_sync;");
+    }
+    const uint32_t taddr =
+        is_tm ? tm_base_s + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)((warp >> 2) * P.tm_cols) : 0u;
+    const int CS = (K + 1) & ~1;   // TMEM columns per word slot
 #if STM_DBG_TIMING
     long long dbg_t[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
 #endif
@@ -528,22 +608,6 @@ __global__ void __launch_bounds__(STM_BFGS_MAX_THREADS, 1) bfgs_kernel(const Est
         const int asp = P.aspect ? P.aspect[d] : 0;
         const float* beta_a = P.beta_t + (size_t)asp * P.V * TS;
 
-        // ---- stage ids / counts, then TMA-gather the beta rows --------------------------------
-        fence_proxy_async();  // previous document's generic writes to this smem precede async writes
-        __syncwarp();
-        if (lane == 0) mbar_expect_tx(mbar, (uint32_t)(n * TS * 4));
-        __syncwarp();
-        double nsum_l = 0.0;
-        for (int v = lane; v < n; v += 32) {
-            const int w = P.word_id[p0 + v];
-            const float c = P.count[p0 + v];
-            cw[v] = c;
-            nsum_l += (double)c;
-            tma_row_g2s(tile + (size_t)v * TS, beta_a + (size_t)w * TS, (uint32_t)(TS * 4), mbar);
-        }
-        const double Nsum = warp_sum(nsum_l);           // np.sum(word_count)       stm.py:955
-        const double Nint = (double)(long long)Nsum;    // int(np.sum(word_count))  stm.py:933
-
         double x[KPL], mu[KPL], p[KPL], g[KPL], gt[KPL], xt[KPL], a[KPL], ex[KPL], xt2[KPL], gt2[KPL];
 #pragma unroll
         for (int i = 0; i < KPL; ++i) {
@@ -552,30 +616,115 @@ __global__ void __launch_bounds__(STM_BFGS_MAX_THREADS, 1) bfgs_kernel(const Est
             mu[i] = (k < K1) ? P.mu[(size_t)d * K1 + k] : 0.0;
             p[i] = 0.0; g[i] = 0.0; gt[i] = 0.0; xt[i] = 0.0; a[i] = 0.0; ex[i] = 0.0; xt2[i] = 0.0; gt2[i] = 0.0;
         }
-        mbar_wait(mbar, parity);
-        parity ^= 1;
-        __syncwarp();
-
-        // ---- a_k = sum_v beta_kv c_v / colsum_v   (eta-independent part of df, stm.py:954) ----
-        for (int v = lane; v < n; v += 32) {
-            const float4* row = reinterpret_cast<const float4*>(tile + (size_t)v * TS);
-            double cs = 0.0;
-            for (int q = 0; q < TS / 4; ++q) {
-                const float4 b = row[q];
-                cs += beta_f2d(b.x); cs += beta_f2d(b.y); cs += beta_f2d(b.z); cs += beta_f2d(b.w);
-            }
-            wv[v] = (double)cw[v] / cs;
-        }
-        __syncwarp();
-        for (int v = 0; v < n; ++v) {
-            const double r = wv[v];
+        double nsum_l = 0.0;
+        float cwr[J];   // TMEM path: counts of this lane's words (slot j <-> word lane + 32 j)
 #pragma unroll
-            for (int i = 0; i < KPL; ++i) {
-                const int k = lane + 32 * i;
-                if (k < K) a[i] += beta_f2d(tile[(size_t)v * TS + k]) * r;
+        for (int j = 0; j < J; ++j) cwr[j] = 0.f;
+        if (is_tm) {
+            // ---- TMEM path: global -> registers -> tcgen05.st, column sums on the way -----------
+            int widr[J];
+            double rv[J];
+            const float4* rowp[J];
+#pragma unroll
+            for (int j = 0; j < J; ++j) {
+                const int v = lane + 32 * j;
+                const bool ok = v < n;
+                widr[j] = ok ? P.word_id[p0 + v] : 0;
+                cwr[j] = ok ? P.count[p0 + v] : 0.f;
+                nsum_l += (double)cwr[j];
+                rowp[j] = reinterpret_cast<const float4*>(beta_a + (size_t)widr[j] * TS);
+                rv[j] = 0.0;   // running column sum, then c_v / colsum_v
             }
+            int c0 = 0;
+            for (; c0 + 8 <= CS; c0 += 8) {
+                float4 b0[J], b1[J];
+#pragma unroll
+                for (int j = 0; j < J; ++j) { b0[j] = __ldg(rowp[j] + (c0 >> 2)); b1[j] = __ldg(rowp[j] + (c0 >> 2) + 1); }
+#pragma unroll
+                for (int j = 0; j < J; ++j) {
+                    rv[j] += beta_f2d(b0[j].x); rv[j] += beta_f2d(b0[j].y); rv[j] += beta_f2d(b0[j].z); rv[j] += beta_f2d(b0[j].w);
+                    rv[j] += beta_f2d(b1[j].x); rv[j] += beta_f2d(b1[j].y); rv[j] += beta_f2d(b1[j].z); rv[j] += beta_f2d(b1[j].w);
+                    tm_st8(taddr + (uint32_t)(j * CS + c0), b0[j], b1[j]);
+                }
+            }
+            if ((CS - c0) & 4) {
+#pragma unroll
+                for (int j = 0; j < J; ++j) {
+                    const float4 b = __ldg(rowp[j] + (c0 >> 2));
+                    rv[j] += beta_f2d(b.x); rv[j] += beta_f2d(b.y); rv[j] += beta_f2d(b.z); rv[j] += beta_f2d(b.w);
+                    tm_st4(taddr + (uint32_t)(j * CS + c0), b);
+                }
+                c0 += 4;
+            }
+            if ((CS - c0) & 2) {
+#pragma unroll
+                for (int j = 0; j < J; ++j) {
+                    const float2 b = __ldg(reinterpret_cast<const float2*>(rowp[j]) + (c0 >> 1));
+                    rv[j] += beta_f2d(b.x); rv[j] += beta_f2d(b.y);
+                    tm_st2(taddr + (uint32_t)(j * CS + c0), b);
+                }
+            }
+            tm_wait_st();
+#pragma unroll
+            for (int j = 0; j < J; ++j) rv[j] = (double)cwr[j] / rv[j];
+            // a_k = sum_v beta_kv c_v / colsum_v (stm.py:954): rows re-read from L2, lane <-> topic
+#pragma unroll
+            for (int j = 0; j < J; ++j) {
+                const int cnt = min(32, n - 32 * j);
+#pragma unroll 4
+                for (int l = 0; l < cnt; ++l) {
+                    const int w = __shfl_sync(STM_FULL, widr[j], l);
+                    const double r = __shfl_sync(STM_FULL, rv[j], l);
+                    const float* row = beta_a + (size_t)w * TS;
+#pragma unroll
+                    for (int i = 0; i < KPL; ++i) {
+                        const int k = lane + 32 * i;
+                        if (k < K) a[i] += beta_f2d(__ldg(row + k)) * r;
+                    }
+                }
+            }
+        } else {
+            // ---- smem path: stage counts, TMA-gather the beta rows ------------------------------
+            fence_proxy_async();  // previous document's generic writes to this smem precede async writes
+            __syncwarp();
+            if (lane == 0) mbar_expect_tx(mbar, (uint32_t)(n * TS * 4));
+            __syncwarp();
+            for (int v = lane; v < n; v += 32) {
+                const int w = P.word_id[p0 + v];
+                const float c = P.count[p0 + v];
+                cw[v] = c;
+                nsum_l += (double)c;
+                tma_row_g2s(tile + (size_t)v * TS, beta_a + (size_t)w * TS, (uint32_t)(TS * 4), mbar);
+            }
+            mbar_wait(mbar, parity);
+            parity ^= 1;
+            __syncwarp();
+            // ---- a_k = sum_v beta_kv c_v / colsum_v   (eta-independent part of df, stm.py:954) ----
+            for (int v = lane; v < n; v += 32) {
+                const float4* row = reinterpret_cast<const float4*>(tile + (size_t)v * TS);
+                double cs = 0.0;
+                for (int q = 0; q < TS / 4; ++q) {
+                    const float4 b = row[q];
+                    cs += beta_f2d(b.x); cs += beta_f2d(b.y); cs += beta_f2d(b.z); cs += beta_f2d(b.w);
+                }
+                wv[v] = (double)cw[v] / cs;
+            }
+            __syncwarp();
+            for (int v = 0; v < n; ++v) {
+                const double r = wv[v];
+#pragma unroll
+                for (int i = 0; i < KPL; ++i) {
+                    const int k = lane + 32 * i;
+                    if (k < K) a[i] += beta_f2d(tile[(size_t)v * TS + k]) * r;
+                }
+            }
+            __syncwarp();
+            // wv may alias v1..v3: restore the zero pads the K-vector reads rely on
+            if (P.n_cap <= 3 * KVS) for (int i = lane; i < 3 * KVS; i += 32) v1[i] = 0.0;
+            __syncwarp();
         }
-        __syncwarp();
+        const double Nsum = warp_sum(nsum_l);           // np.sum(word_count)       stm.py:955
+        const double Nint = (double)(long long)Nsum;    // int(np.sum(word_count))  stm.py:933
 
         // =======================================================================================
         // BFGS (scipy/optimize/_optimize.py:1345-1526) as a warp-uniform state machine with ONE
@@ -664,35 +813,92 @@ __global__ void __launch_bounds__(STM_BFGS_MAX_THREADS, 1) bfgs_kernel(const Est
                     logprod_init(lp);
                     for (int w0 = 0; w0 < n; w0 += 32 * J) {
                         double acc[J][2];
-                        const float4* rows[J];
+                        float cj[J];
 #pragma unroll
-                        for (int j = 0; j < J; ++j) {
-                            acc[j][0] = 0.0; acc[j][1] = 0.0;
-                            int v = w0 + lane + 32 * j;
-                            if (v >= n) v = n - 1;
-                            rows[j] = reinterpret_cast<const float4*>(tile + (size_t)v * TS);
-                        }
-                        const double2* e2 = reinterpret_cast<const double2*>(v0);
-                        STM_UNROLL_Q
-                        for (int q = 0; q < TS / 4; ++q) {
-                            const double2 ea = e2[2 * q], eb = e2[2 * q + 1];
+                        for (int j = 0; j < J; ++j) { acc[j][0] = 0.0; acc[j][1] = 0.0; }
+                        if (is_tm) {
+                            // tile in TMEM: lane <-> word (slot j), 8 topics per tcgen05.ld (one pass: n <= 32 J)
+                            const double2* e2 = reinterpret_cast<const double2*>(v0);
+                            int c0 = 0;
+#pragma unroll 1
+                            for (; c0 + 8 <= CS; c0 += 8) {
+                                uint32_t b[J][8];
+#pragma unroll
+                                for (int j = 0; j < J; ++j) tm_ld8(taddr + (uint32_t)(j * CS + c0), b[j]);
+                                const double2 e0 = e2[(c0 >> 1)], e1 = e2[(c0 >> 1) + 1], e2_ = e2[(c0 >> 1) + 2], e3 = e2[(c0 >> 1) + 3];
+                                tm_wait_ld();
+#pragma unroll
+                                for (int j = 0; j < J; ++j) {
+                                    acc[j][0] = fma(e0.x, beta_u2d(b[j][0]), acc[j][0]);
+                                    acc[j][1] = fma(e0.y, beta_u2d(b[j][1]), acc[j][1]);
+                                    acc[j][0] = fma(e1.x, beta_u2d(b[j][2]), acc[j][0]);
+                                    acc[j][1] = fma(e1.y, beta_u2d(b[j][3]), acc[j][1]);
+                                    acc[j][0] = fma(e2_.x, beta_u2d(b[j][4]), acc[j][0]);
+                                    acc[j][1] = fma(e2_.y, beta_u2d(b[j][5]), acc[j][1]);
+                                    acc[j][0] = fma(e3.x, beta_u2d(b[j][6]), acc[j][0]);
+                                    acc[j][1] = fma(e3.y, beta_u2d(b[j][7]), acc[j][1]);
+                                }
+                            }
+                            if ((CS - c0) & 4) {
+                                uint32_t b[J][4];
+#pragma unroll
+                                for (int j = 0; j < J; ++j) tm_ld4(taddr + (uint32_t)(j * CS + c0), b[j]);
+                                const double2 e0 = e2[(c0 >> 1)], e1 = e2[(c0 >> 1) + 1];
+                                tm_wait_ld();
+#pragma unroll
+                                for (int j = 0; j < J; ++j) {
+                                    acc[j][0] = fma(e0.x, beta_u2d(b[j][0]), acc[j][0]);
+                                    acc[j][1] = fma(e0.y, beta_u2d(b[j][1]), acc[j][1]);
+                                    acc[j][0] = fma(e1.x, beta_u2d(b[j][2]), acc[j][0]);
+                                    acc[j][1] = fma(e1.y, beta_u2d(b[j][3]), acc[j][1]);
+                                }
+                                c0 += 4;
+                            }
+                            if ((CS - c0) & 2) {
+                                uint32_t b[J][2];
+#pragma unroll
+                                for (int j = 0; j < J; ++j) tm_ld2(taddr + (uint32_t)(j * CS + c0), b[j]);
+                                const double2 e0 = e2[(c0 >> 1)];
+                                tm_wait_ld();
+#pragma unroll
+                                for (int j = 0; j < J; ++j) {
+                                    acc[j][0] = fma(e0.x, beta_u2d(b[j][0]), acc[j][0]);
+                                    acc[j][1] = fma(e0.y, beta_u2d(b[j][1]), acc[j][1]);
+                                }
+                            }
+#pragma unroll
+                            for (int j = 0; j < J; ++j) cj[j] = cwr[j];
+                        } else {
+                            const float4* rows[J];
 #pragma unroll
                             for (int j = 0; j < J; ++j) {
-                                const float4 b = rows[j][q];
-                                acc[j][0] = fma(ea.x, beta_f2d(b.x), acc[j][0]);
-                                acc[j][1] = fma(ea.y, beta_f2d(b.y), acc[j][1]);
-                                acc[j][0] = fma(eb.x, beta_f2d(b.z), acc[j][0]);
-                                acc[j][1] = fma(eb.y, beta_f2d(b.w), acc[j][1]);
+                                                            int v = w0 + lane + 32 * j;
+                                if (v >= n) v = n - 1;
+                                rows[j] = reinterpret_cast<const float4*>(tile + (size_t)v * TS);
+                            }
+                            const double2* e2 = reinterpret_cast<const double2*>(v0);
+                            STM_UNROLL_Q
+                            for (int q = 0; q < TS / 4; ++q) {
+                                const double2 ea = e2[2 * q], eb = e2[2 * q + 1];
+#pragma unroll
+                                for (int j = 0; j < J; ++j) {
+                                    const float4 b = rows[j][q];
+                                    acc[j][0] = fma(ea.x, beta_f2d(b.x), acc[j][0]);
+                                    acc[j][1] = fma(ea.y, beta_f2d(b.y), acc[j][1]);
+                                    acc[j][0] = fma(eb.x, beta_f2d(b.z), acc[j][0]);
+                                    acc[j][1] = fma(eb.y, beta_f2d(b.w), acc[j][1]);
+                                }
+                            }
+#pragma unroll
+                            for (int j = 0; j < J; ++j) {
+                                const int v = w0 + lane + 32 * j;
+                                cj[j] = (v < n) ? cw[v] : 0.f;
                             }
                         }
 #pragma unroll
                         for (int j = 0; j < J; ++j) {
                             const int v = w0 + lane + 32 * j;
-#if STM_LOGPROD
-                            if (v < n) logprod_add(lp, acc[j][0] + acc[j][1], cw[v]);
-#else
-                            if (v < n) lp.extra += (double)cw[v] * log(acc[j][0] + acc[j][1]);
-#endif
+                            if (v < n) logprod_add(lp, acc[j][0] + acc[j][1], cj[j]);
                         }
                         logprod_renorm(lp);
                     }
@@ -1035,6 +1241,11 @@ __global__ void __launch_bounds__(STM_BFGS_MAX_THREADS, 1) bfgs_kernel(const Est
     if (lane == 0)
         for (int i = 0; i < 16; ++i) atomicAdd(P.dbg_cycles + i, (unsigned long long)dbg_t[i]);
 #endif
+    if (P.tm_warps > 0) {
+        asm volatile("tcgen05.fence::before_thread_sync;");
+        __syncthreads();
+        if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tm_base_s));
+    }
 }
 
 // ===== POST KERNEL =====

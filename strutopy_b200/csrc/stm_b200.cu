@@ -26,6 +26,7 @@ struct LengthClass {
     int* d_docs = nullptr;
     // kernel A (BFGS) / kernel B (post-optimisation): warps per CTA, bytes of shared memory per warp, CTAs
     int warps = 0, smem_per_warp = 0, grid = 0;
+    int smem_small = 0, tm_warps = 0, tm_cols = 0;   // kernel A: small block bytes, TMEM-resident warps / columns each
     int post_warps = 0, post_smem_per_warp = 0, post_grid = 0;
 };
 
@@ -103,12 +104,17 @@ int beta_stride(int K) {
     return ts;
 }
 
-// mirrors the carve-up at the top of stm::bfgs_kernel
-size_t bfgs_smem_per_warp(int n_cap, int TS, int KPL) {
+// mirror the carve-up at the top of stm::bfgs_kernel: a small block per warp (K-vectors, line-search
+// state, mbarrier) and a tile block per warp whose tile lives in shared memory (not TMEM)
+size_t bfgs_smem_small(int KPL) {
+    const int KVS = KPL * 32 + 8;
+    const size_t total = (size_t)4 * KVS * 8 + sizeof(stm::LsState) + 8;
+    return (total + 127) & ~(size_t)127;
+}
+size_t bfgs_smem_tile(int n_cap, int TS, int KPL) {
     const size_t tile = ((size_t)n_cap * TS * 4 + 127) & ~(size_t)127;
     const int KVS = KPL * 32 + 8;
-    const size_t total = tile + (size_t)n_cap * 8 + (size_t)4 * KVS * 8 + sizeof(stm::LsState) +
-                         (size_t)((n_cap + 1) & ~1) * 4 + 8;
+    const size_t total = tile + (size_t)((n_cap + 1) & ~1) * 4 + (n_cap > 3 * KVS ? (size_t)n_cap * 8 : 0);
     return (total + 127) & ~(size_t)127;
 }
 // mirrors the carve-up at the top of stm::post_kernel
@@ -527,8 +533,26 @@ int stm_set_corpus(stm_ctx* ctx, int64_t D, const int64_t* doc_ptr, const int32_
         std::stable_sort(members[ci].begin(), members[ci].end(), [&](int a, int b) {
             return (doc_ptr[a + 1] - doc_ptr[a]) > (doc_ptr[b + 1] - doc_ptr[b]);
         });
-        lc.smem_per_warp = (int)bfgs_smem_per_warp(lc.n_cap, ctx->TS, ctx->KPL);
-        lc.warps = std::min(STM_BFGS_MAX_THREADS / 32, ctx->max_smem / lc.smem_per_warp);
+        lc.smem_per_warp = (int)bfgs_smem_tile(lc.n_cap, ctx->TS, ctx->KPL);
+        lc.smem_small = (int)bfgs_smem_small(ctx->KPL);
+        {
+            // TMEM residency: a warp's lanes hold ceil(n_cap/32) word slots of CS columns each; 8 warps
+            // x 256 columns or 4 warps x 512 columns (a warp can only address its own 32-lane quarter)
+            const int slots = (lc.n_cap + 31) / 32, CS = (ctx->K + 1) & ~1;
+            if (lc.n_cap <= 32 * lc.J) {
+                if (slots * CS <= 256) { lc.tm_warps = 8; lc.tm_cols = 256; }
+                else if (slots * CS <= 512) { lc.tm_warps = 4; lc.tm_cols = 512; }
+            }
+            if (const char* e = getenv("STM_TM_WARPS")) {  // development knob
+                const int c = atoi(e);
+                if (c == 0 || (c == 4 && lc.tm_warps >= 4)) { lc.tm_warps = c; lc.tm_cols = c ? 512 : 0; }
+            }
+            const int max_w = STM_BFGS_MAX_THREADS / 32;
+            const int avail = ctx->max_smem - 128 - lc.tm_warps * lc.smem_small;   // 128: static shared (TMEM base)
+            int sw = avail > 0 ? avail / (lc.smem_small + lc.smem_per_warp) : 0;
+            sw = std::max(0, std::min(sw, max_w - lc.tm_warps));
+            lc.warps = lc.tm_warps + sw;
+        }
         lc.post_smem_per_warp = (int)post_smem_per_warp(lc.n_cap, ctx->TS, ctx->K1, ctx->KPL);
         lc.post_warps = std::min(8, ctx->max_smem / lc.post_smem_per_warp);
         if (const char* cap = getenv("STM_MAX_WARPS")) {  // development knob (occupancy experiments)
@@ -541,7 +565,7 @@ int stm_set_corpus(stm_ctx* ctx, int64_t D, const int64_t* doc_ptr, const int32_
                             " bytes) does not fit in shared memory");
         lc.grid = std::min(ctx->sm_count, (lc.n_docs + lc.warps - 1) / lc.warps);
         lc.post_grid = std::min(ctx->sm_count, (lc.n_docs + lc.post_warps - 1) / lc.post_warps);
-        max_warps = std::max(max_warps, lc.post_grid * lc.post_warps);
+        max_warps = std::max(max_warps, std::max(lc.grid * lc.warps, lc.post_grid * lc.post_warps));
         CU(cudaMalloc(&lc.d_docs, sizeof(int) * lc.n_docs));
         CU(cudaMemcpy(lc.d_docs, members[ci].data(), sizeof(int) * lc.n_docs, cudaMemcpyHostToDevice));
         max_warps = std::max(max_warps, lc.grid * lc.warps);
@@ -634,10 +658,11 @@ int stm_estep(stm_ctx* ctx, const float* beta_t_dev, const double* mu_dev, const
         P.sigma_ss_rep = ctx->d_sigma_rep; P.n_rep = ctx->n_rep;
         P.scratch = ctx->d_scratch; P.scratch_stride = ctx->scratch_stride;
         P.n_cap = lc.n_cap; P.smem_per_warp = lc.smem_per_warp;
+        P.smem_small = lc.smem_small; P.tm_warps = lc.tm_warps; P.tm_cols = lc.tm_cols;
         P.dbg_cycles = ctx->d_dbg;
         static const int dev_skip = getenv("STM_DEV_SKIP") ? atoi(getenv("STM_DEV_SKIP")) : 0;  // 1: no kernel A, 2: no kernel B (timing only)
         if (dev_skip != 1)
-            CU(launch_bfgs(ctx->KPL, P, lc.J, lc.grid, lc.warps * 32, (size_t)lc.smem_per_warp * lc.warps, st));
+            CU(launch_bfgs(ctx->KPL, P, lc.J, lc.grid, lc.warps * 32, (size_t)lc.smem_small * lc.warps + (size_t)lc.smem_per_warp * (lc.warps - lc.tm_warps), st));
         P.queue = ctx->d_queues + 16 + ci;
         P.smem_per_warp = lc.post_smem_per_warp;
         if (dev_skip != 2)
