@@ -36,3 +36,18 @@ cudaError_t STM_CAT(stm_launch_post_kpl, STM_KPL)(const stm::EstepParams& P, int
     stm::post_kernel<STM_KPL><<<grid, block, smem, st>>>(P);
     return cudaGetLastError();
 }
+
+// group version of kernel B (3 warps per document, K-1 <= 52); only instantiated where it applies
+cudaError_t STM_CAT(stm_launch_post_group_kpl, STM_KPL)(const stm::EstepParams& P, int grid, int block, size_t smem,
+                                                        cudaStream_t st) {
+#if STM_KPL <= 2
+    cudaError_t e = cudaFuncSetAttribute(stm::post_group_kernel<STM_KPL>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    stm::post_group_kernel<STM_KPL><<<grid, block, smem, st>>>(P);
+    return cudaGetLastError();
+#else
+    (void)P; (void)grid; (void)block; (void)smem; (void)st;
+    return cudaErrorNotSupported;
+#endif
+}

@@ -1608,4 +1608,407 @@ __global__ void __launch_bounds__(256, 1) post_kernel(const EstepParams P) {
 #endif
 }
 
+
+// ===== POST KERNEL, GROUP VERSION =====
+// Kernel B for K-1 <= 52: THREE warps (96 threads) per document, up to 6 documents per CTA, so the
+// post-optimisation work runs at 18 warps per SM instead of 6 and its dense part is parallel:
+//   * Hessian data term: DMMA row-blocks dealt to the 3 warps (snake order, balanced), phi scattered
+//     and row sums taken by the warp that owns the row block;
+//   * PD test, Cholesky pivots, nu = H^-1 in ONE pass: the symmetric SWEEP operator
+//     (B_kk = -1/A_kk, B_ik = A_ik/A_kk, B_ij = A_ij - A_ik A_kj/A_kk; after all pivots B = -A^-1),
+//     each thread holding a 4x4 patch of the lower triangle in REGISTERS (13*14/2 = 91 patches);
+//     pivot k equals the Cholesky pivot L_kk^2, so "np.linalg.cholesky succeeds" (stm.py:1017, 1040)
+//     is "all pivots > 0" and sum log L_ii = 1/2 sum log d_k;
+//   * nu leaves the registers as fp64 reductions into the replicated sigma_ss accumulators.
+constexpr int POST_GW = 3;              // warps per document
+constexpr int POST_GT = POST_GW * 32;   // threads per document
+constexpr int POST_NPATCH = 91;         // 4x4 patches of the lower triangle of a 52x52 matrix
+constexpr int POST_UST = 56;            // stride of the small fp64 vectors (Dg, u, d)
+#ifndef STM_POST_MAX_THREADS
+#define STM_POST_MAX_THREADS 576        // 6 groups of 96 threads -> 112 registers per thread
+#endif
+
+__device__ __forceinline__ void group_bar(int grp) {
+    asm volatile("bar.sync %0, %1;" ::"r"(grp + 1), "r"(POST_GT) : "memory");
+}
+// sum over the 96 threads of a group; red = 4 doubles of group-private shared memory
+__device__ __forceinline__ double group_sum(double v, double* red, int wg, int lane, int grp) {
+    v = warp_sum(v);
+    if (lane == 0) red[wg] = v;
+    group_bar(grp);
+    const double r = (red[0] + red[1]) + red[2];
+    group_bar(grp);
+    return r;
+}
+
+template <int KPL>
+__global__ void __launch_bounds__(STM_POST_MAX_THREADS, 1) post_group_kernel(const EstepParams P) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int grp = threadIdx.x / POST_GT;
+    const int gt = threadIdx.x - grp * POST_GT;
+    const int wg = gt >> 5, lane = gt & 31;
+    const int K = P.K, K1 = K - 1, TS = P.TS;
+    constexpr int KV = KPL * 32;
+    constexpr int KVS = KV + 8;
+    constexpr int NBMAX = 4 * KPL;
+    const int HS = K1 | 1;
+
+    // ---- per-group shared memory carve-up (post_group_smem in stm_b200.cu mirrors this) --------
+    unsigned char* base = smem_raw + (size_t)grp * P.smem_per_warp;
+    size_t tile_bytes = (size_t)(P.n_cap + 1) * TS * 4;   // + 1 row: the last 8-topic block may read past a row's end
+    const size_t h_bytes = (size_t)K1 * HS * 8;
+    if (h_bytes > tile_bytes) tile_bytes = h_bytes;
+    tile_bytes = (tile_bytes + 127) & ~(size_t)127;
+    float* tile = reinterpret_cast<float*>(base);
+    double* Hm = reinterpret_cast<double*>(base);   // aliases the tile once it is dead
+    size_t w_bytes = (size_t)P.n_cap * 16;
+    if (w_bytes < (size_t)4 * POST_UST * 8) w_bytes = (size_t)4 * POST_UST * 8;
+    double* wv = reinterpret_cast<double*>(base + tile_bytes);   // [n_cap] sqrt(c_v)/colsum_v
+    double* wv2 = wv + P.n_cap;                                  // [n_cap] sqrt(c_v)
+    double* Dg = wv;                      // the dense phase re-uses the per-word block:
+    double* ubuf = wv + POST_UST;         //   diagonal, 2 pivot vectors, pivots
+    double* dvec = wv + 3 * POST_UST;
+    double* vec = reinterpret_cast<double*>(base + tile_bytes + w_bytes);   // [4][KVS]
+    double* red = vec + 4 * KVS;                                            // [8] reductions / scalars
+    float* cw = reinterpret_cast<float*>(red + 8);
+    int* wid = reinterpret_cast<int*>(cw + P.n_cap);
+    uint64_t* mbar = reinterpret_cast<uint64_t*>(wid + ((P.n_cap + 1) & ~1));
+    int* qslot = reinterpret_cast<int*>(mbar + 1);
+    double* v0 = vec;            // exp(eta~)
+    double* v1 = vec + KVS;      // theta * exp(eta~)
+    double* v2 = vec + 2 * KVS;  // theta (stable softmax)
+    double* v3 = vec + 3 * KVS;  // row sums of phi
+    for (int i = gt; i < 4 * KVS; i += POST_GT) vec[i] = 0.0;
+    if (gt == 0) mbar_init(mbar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    group_bar(grp);
+    uint32_t parity = 0;
+
+    const int ggrp = blockIdx.x * (blockDim.x / POST_GT) + grp;
+    double* Hg = P.scratch + (size_t)ggrp * P.scratch_stride + (size_t)K1 * K1;   // Hessian bounce (L2)
+    double* sig_acc = P.sigma_ss_rep + (size_t)(ggrp % P.n_rep) * K1 * K1;
+
+    // this thread's 4x4 patch of the lower triangle
+    const bool has_patch = gt < POST_NPATCH;
+    int pi = 0, pj = 0;
+    if (has_patch) {
+        while ((pi + 1) * (pi + 2) / 2 <= gt) pi++;
+        pj = gt - pi * (pi + 1) / 2;
+    }
+    double Sd[KPL];
+#pragma unroll
+    for (int i = 0; i < KPL; ++i) {
+        const int k = lane + 32 * i;
+        Sd[i] = (k < K1) ? P.prior[k] : 0.0;
+    }
+    const double sigmaentropy = P.prior[K1];
+
+    for (;;) {
+        if (gt == 0) *qslot = (int)atomicAdd(P.queue, 1u);
+        fence_proxy_async();   // the previous document's generic smem accesses precede the async writes
+        group_bar(grp);
+        const int qi = *qslot;
+        if (qi >= P.n_docs) break;
+        const int d = P.docs[qi];
+        const long long p0 = P.doc_ptr[d];
+        const int n = (int)(P.doc_ptr[d + 1] - p0);
+        const int asp = P.aspect ? P.aspect[d] : 0;
+        const float* beta_a = P.beta_t + (size_t)asp * P.V * TS;
+        double* beta_ss_a = P.beta_ss_t + (size_t)asp * P.V * TS;
+
+        // ---- gather: ids / counts, TMA bulk copies of the beta rows -----------------------------
+        if (gt == 0) mbar_expect_tx(mbar, (uint32_t)(n * TS * 4));
+        double nsum_l = 0.0;
+        for (int v = gt; v < n; v += POST_GT) {
+            const int w = P.word_id[p0 + v];
+            const float c = P.count[p0 + v];
+            wid[v] = w;
+            cw[v] = c;
+            nsum_l += (double)c;
+            tma_row_g2s(tile + (size_t)v * TS, beta_a + (size_t)w * TS, (uint32_t)(TS * 4), mbar);
+        }
+        if (gt < 8) tile[(size_t)n * TS + gt] = 0.f;   // what the last word's last topic block over-reads
+        const double Nsum = group_sum(nsum_l, red, wg, lane, grp);   // np.sum(word_count)
+
+        // ---- theta (stm.py:546-549, 905-909) and the prior quadratic, by the group's first warp ---
+        double th[KPL];
+        if (wg == 0) {
+            double x[KPL], et[KPL], eu[KPL], m = -INFINITY, se_l = 0.0, ss_l = 0.0, q_l = 0.0;
+#pragma unroll
+            for (int i = 0; i < KPL; ++i) {
+                const int k = lane + 32 * i;
+                x[i] = (k < K1) ? P.eta[(size_t)d * K1 + k] : 0.0;
+                const double mu = (k < K1) ? P.mu[(size_t)d * K1 + k] : 0.0;
+                const double dk = x[i] - mu;
+                q_l += (Sd[i] * dk) * dk;
+                et[i] = (k < K1) ? x[i] : ((k == K1) ? 0.0 : -INFINITY);
+                m = nanmax(m, et[i]);
+            }
+            m = warp_max(m);
+#pragma unroll
+            for (int i = 0; i < KPL; ++i) {
+                eu[i] = exp(et[i]);
+                th[i] = exp(et[i] - m);
+                se_l += eu[i];
+                ss_l += th[i];
+            }
+            const double se = warp_sum(se_l), ss = warp_sum(ss_l);
+            const double quad = warp_sum(q_l);
+#pragma unroll
+            for (int i = 0; i < KPL; ++i) {
+                const int k = lane + 32 * i;
+                th[i] = th[i] / ss;
+                if (k < K) P.theta[(size_t)d * K + k] = eu[i] / se;  // stm.py:547-549 (no max shift)
+                v0[k] = (k < K) ? eu[i] : 0.0;
+                v1[k] = (k < K) ? th[i] * eu[i] : 0.0;
+                v2[k] = (k < K) ? th[i] : 0.0;
+            }
+            if (lane == 0) red[4] = quad;
+        }
+        mbar_wait(mbar, parity);
+        parity ^= 1;
+        group_bar(grp);
+
+        // ---- colsum_v = sum_k e_k beta_kv, log-likelihood part of the bound (stm.py:1088-1096) ----
+        double loglik;
+        {
+            LogProd lp;
+            logprod_init(lp);
+            const double2* e2 = reinterpret_cast<const double2*>(v0);
+            const double2* t2 = reinterpret_cast<const double2*>(v1);
+#pragma unroll 1
+            for (int v = gt; v < n; v += POST_GT) {
+                const float4* row = reinterpret_cast<const float4*>(tile + (size_t)v * TS);
+                double s0 = 0.0, s1 = 0.0, t0 = 0.0, t1 = 0.0;
+#pragma unroll 1
+                for (int q = 0; q < TS / 4; ++q) {
+                    const float4 bq = row[q];
+                    const double2 ea = e2[2 * q], eb = e2[2 * q + 1], wa = t2[2 * q], wb = t2[2 * q + 1];
+                    const double b0 = beta_f2d(bq.x), b1 = beta_f2d(bq.y), b2 = beta_f2d(bq.z), b3 = beta_f2d(bq.w);
+                    s0 = fma(ea.x, b0, s0); t0 = fma(wa.x, b0, t0);
+                    s1 = fma(ea.y, b1, s1); t1 = fma(wa.y, b1, t1);
+                    s0 = fma(eb.x, b2, s0); t0 = fma(wb.x, b2, t0);
+                    s1 = fma(eb.y, b3, s1); t1 = fma(wb.y, b3, t1);
+                }
+                const float cf = cw[v];
+                logprod_add(lp, t0 + t1, cf);
+                logprod_renorm(lp);
+                const double sq = sqrt((double)cf);
+                wv[v] = sq / (s0 + s1);   // sqrt(c_v)/colsum_v
+                wv2[v] = sq;
+            }
+            loglik = group_sum(logprod_value(lp), red, wg, lane, grp);   // also publishes wv / wv2
+        }
+
+        // ---- Hessian data term sum_v b_v b_v' (stm.py:1000-1006) on the fp64 tensor cores (DMMA
+        // m8n8k4, four words per step), one 8-topic row block at a time; phi -> beta_ss
+        // (stm.py:1103-1118, 582-590) and its row sums by the warp that owns the row block ---------
+        {
+            const int nbp = (K + 7) >> 3;
+            const int w4 = lane & 3, kk = lane >> 2;
+            double ek[NBMAX];   // exp(eta~) of this lane's topics (zero beyond K)
+#pragma unroll
+            for (int t = 0; t < NBMAX; ++t) ek[t] = v0[8 * t + kk];
+            int qpos = 0;
+#pragma unroll 1
+            for (int br = nbp - 1; br >= 0; --br, ++qpos) {
+                const int m6 = qpos % (2 * POST_GW);
+                if ((m6 < POST_GW ? m6 : 2 * POST_GW - 1 - m6) != wg) continue;
+                double acc[NBMAX][2];
+#pragma unroll
+                for (int bc = 0; bc < NBMAX; ++bc) { acc[bc][0] = 0.0; acc[bc][1] = 0.0; }
+                double rs = 0.0;
+                const int kb = 8 * br + kk;
+                const double ekb = v0[kb];
+                const bool kok = kb < K;
+                double* ssb = beta_ss_a + kb;
+#define STM_FR(t) fr[t] = (beta_f2d(tb[8 * (t)]) * ek[t]) * sc;
+#define STM_MMA(t)                                                                               \
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" \
+                 : "+d"(acc[t][0]), "+d"(acc[t][1])                                              \
+                 : "d"(fa), "d"(fr[t]));
+#pragma unroll 1
+                for (int vb = 0; vb < n; vb += 4) {
+                    const int v = vb + w4;
+                    const bool vok = v < n;
+                    const int vc = vok ? v : 0;
+                    const double sc = vok ? wv[vc] : 0.0;
+                    const float* tb = tile + (size_t)vc * TS + kk;
+                    double fr[NBMAX];
+                    // fr[t] for t <= br (fall-through: no per-block guards; reads past the row end hit the
+                    // next row / the zeroed spare row and are multiplied by ek = 0)
+                    switch (br) {
+                        case 7: if (NBMAX > 7) { STM_FR(NBMAX > 7 ? 7 : 0) }
+                        case 6: if (NBMAX > 6) { STM_FR(NBMAX > 6 ? 6 : 0) }
+                        case 5: if (NBMAX > 5) { STM_FR(NBMAX > 5 ? 5 : 0) }
+                        case 4: if (NBMAX > 4) { STM_FR(NBMAX > 4 ? 4 : 0) }
+                        case 3: STM_FR(3)
+                        case 2: STM_FR(2)
+                        case 1: STM_FR(1)
+                        default: STM_FR(0)
+                    }
+                    const double fa = (beta_f2d(tb[8 * br]) * ekb) * sc;
+                    if (vok && kok) {
+                        const double ph = fa * wv2[vc];
+                        rs += ph;
+                        if (!STM_DBG_NO_PHI) red_add_f64(ssb + (size_t)wid[vc] * TS, ph);
+                    }
+                    switch (br) {
+                        case 7: if (NBMAX > 7) { STM_MMA(NBMAX > 7 ? 7 : 0) }
+                        case 6: if (NBMAX > 6) { STM_MMA(NBMAX > 6 ? 6 : 0) }
+                        case 5: if (NBMAX > 5) { STM_MMA(NBMAX > 5 ? 5 : 0) }
+                        case 4: if (NBMAX > 4) { STM_MMA(NBMAX > 4 ? 4 : 0) }
+                        case 3: STM_MMA(3)
+                        case 2: STM_MMA(2)
+                        case 1: STM_MMA(1)
+                        default: STM_MMA(0)
+                    }
+                }
+#undef STM_FR
+#undef STM_MMA
+                // C fragment: row = lane>>2, cols = 2*(lane&3) + {0,1}
+                const int gi = br * 8 + kk;
+#pragma unroll
+                for (int bc = 0; bc < NBMAX; ++bc) {
+                    if (bc <= br) {
+#pragma unroll
+                        for (int c = 0; c < 2; ++c) {
+                            const int gj = bc * 8 + 2 * w4 + c;
+                            if (gi < K1 && gj <= gi) Hg[(size_t)gi * K1 + gj] = acc[bc][c];
+                        }
+                    }
+                }
+                rs += __shfl_xor_sync(STM_FULL, rs, 1);
+                rs += __shfl_xor_sync(STM_FULL, rs, 2);
+                if (w4 == 0 && kb < KV) v3[kb] = rs;
+            }
+        }
+        group_bar(grp);   // tile dead; Hg and v3 complete
+
+        // ---- assemble H = data - N theta theta' + diag(-rowsum + N theta) + siginv (stm.py:1007-1015)
+        for (int r = wg; r < K1; r += POST_GW) {
+            const double thr = v2[r];
+            for (int k = lane; k <= r; k += 32) {
+                const double thk = v2[k];
+                double h = __ldcg(&Hg[(size_t)r * K1 + k]) - Nsum * (thr * thk);
+                if (k == r) {
+                    h = (h - v3[k] + Nsum * thk) + P.prior[k];
+                    Dg[k] = h;
+                }
+                Hm[(size_t)r * HS + k] = h;
+                Hm[(size_t)k * HS + r] = h;
+            }
+        }
+        group_bar(grp);
+
+        // ---- PD test + repairs (stm.py:1017-1021, 1039-1048) and the inverse, by sweeping ----------
+        int repair = 0, upper = 0, dead = 0;
+        double a[4][4];
+        for (int attempt = 0;; ++attempt) {
+#pragma unroll
+            for (int r = 0; r < 4; ++r)
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    const int i = 4 * pi + r, j = 4 * pj + c;
+                    a[r][c] = (has_patch && i < K1 && j < K1) ? ((i == j) ? Dg[i] : Hm[(size_t)i * HS + j])
+                                                              : ((i == j) ? 1.0 : 0.0);
+                }
+            int ok = 1;
+#pragma unroll 1
+            for (int kb = 0; 4 * kb < K1 && ok; ++kb) {
+#pragma unroll
+                for (int kr = 0; kr < 4; ++kr) {
+                    const int k = 4 * kb + kr;
+                    if (k < K1 && ok) {
+                        double* ub = ubuf + (k & 1) * POST_UST;
+                        if (has_patch) {
+                            if (pi == kb) {
+#pragma unroll
+                                for (int c = 0; c < 4; ++c) ub[4 * pj + c] = a[kr][c];
+                            } else if (pj == kb) {
+#pragma unroll
+                                for (int r = 0; r < 4; ++r) ub[4 * pi + r] = a[r][kr];
+                            }
+                        }
+                        group_bar(grp);
+                        const double dk = ub[k];
+                        if (!(dk > 0.0)) {
+                            ok = 0;
+                        } else {
+                            if (gt == 0) dvec[k] = dk;
+                            const double pv = ddiv(1.0, dk);
+                            if (has_patch) {
+                                double ui[4], upj[4];
+#pragma unroll
+                                for (int r = 0; r < 4; ++r) { ui[r] = ub[4 * pi + r]; upj[r] = ub[4 * pj + r] * pv; }
+#pragma unroll
+                                for (int r = 0; r < 4; ++r)
+#pragma unroll
+                                    for (int c = 0; c < 4; ++c) a[r][c] = fma(-ui[r], upj[c], a[r][c]);
+                                if (pi == kb) {
+#pragma unroll
+                                    for (int c = 0; c < 4; ++c) a[kr][c] = upj[c];
+                                }
+                                if (pj == kb) {
+#pragma unroll
+                                    for (int r = 0; r < 4; ++r) a[r][kr] = ui[r] * pv;
+                                    if (pi == kb) a[kr][kr] = -pv;
+                                }
+                            }
+                        }
+                    }
+                }
+            }
+            if (ok) break;
+            group_bar(grp);   // every thread has left the sweep before Dg changes
+            if (attempt == 0 || attempt == 2 || attempt == 3) {
+                // make_pd (stm.py:964-984): d_i <- max(d_i, sum_j!=i |H_ij|)
+                for (int i = gt; i < K1; i += POST_GT) {
+                    double tot = 0.0;
+                    for (int k = 0; k < K1; ++k) if (k != i) tot += fabs(Hm[(size_t)i * HS + k]);
+                    tot += fabs(Dg[i]);
+                    const double mag = tot - fabs(Dg[i]);
+                    if (Dg[i] < mag) Dg[i] = mag;
+                }
+            }
+            if (attempt == 1 || attempt == 3) {
+                for (int i = gt; i < K1; i += POST_GT) Dg[i] += 1e-5;
+            }
+            if (attempt == 0) repair = 1;            // hessian(): make_pd
+            else if (attempt == 1) repair = 2;       // hessian(): + 1e-5
+            else if (attempt == 2) repair += 4;      // decompose_hessian(): make_pd
+            else if (attempt == 3) { repair += 8; upper = 1; }  // scipy.linalg.cholesky (upper) of make_pd + 1e-5 I
+            else { dead = 1; break; }
+            group_bar(grp);
+        }
+        group_bar(grp);   // dvec complete
+
+        // ---- bound (stm.py:1085-1100): sum log L_ii = 1/2 sum log d_k ------------------------------
+        double lg = 0.0;
+        if (gt < K1) lg = dead ? nan("") : log_noinline(dvec[gt]);
+        const double logdet_half = 0.5 * group_sum(lg, red, wg, lane, grp);
+        if (gt == 0) {
+            P.doc_bound[d] = loglik - logdet_half - 0.5 * red[4] - sigmaentropy;
+            P.doc_info[d] = (P.doc_info[d] & 0xffffff) | (repair << 24);
+        }
+        // ---- nu = H^-1 (stm.py:1052-1066, accumulated stm.py:582): the swept matrix is -H^-1 --------
+        if (has_patch) {
+#pragma unroll
+            for (int r = 0; r < 4; ++r)
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    const int i = 4 * pi + r, j = 4 * pj + c;
+                    if (i < K1 && j <= i) {
+                        double nu;
+                        if (dead) nu = nan("");
+                        else if (!upper) nu = -a[r][c];
+                        // scipy's UPPER factor in optimize_nu: only its diagonal survives np.triu(L.T)
+                        else nu = (i == j) ? 1.0 / dvec[i] : 0.0;
+                        if (!upper || i == j) red_add_f64(sig_acc + (size_t)i * K1 + j, nu);
+                    }
+                }
+        }
+    }  // document loop
+}
+
 }  // namespace stm
