@@ -1641,12 +1641,47 @@ __device__ __forceinline__ double group_sum(double v, double* red, int wg, int l
     return r;
 }
 
+// One row block (8 topics, BR static) of the Hessian data term over all words of a document, on the
+// fp64 tensor cores: mma.sync m8n8k4, four words per step.  Lane (w4 = lane&3, kk = lane>>2) computes
+// b = beta e sqrt(c)/colsum for word vb+w4 and topic 8t+kk: exactly its A-fragment element of row
+// block t AND its B-fragment element of column block t.  The owner of the row block also scatters
+// phi = b sqrt(c) into beta_ss and takes its row sums.
+template <int NBMAX, int BR>
+__device__ __forceinline__ void hess_row_pass(const float* tile, int TS, int n, const double* wv, const double* wv2,
+                                              const int* wid, const double (&ek)[NBMAX], double ekb, bool kok,
+                                              double* ssb, int w4, int kk, double (&acc)[NBMAX][2], double& rs) {
+#pragma unroll 1
+    for (int vb = 0; vb < n; vb += 4) {
+        const int v = vb + w4;
+        const double sc = wv[v];                      // zero for the (< 4) slots past the last word
+        const float* tb = tile + (size_t)min(v, n - 1) * TS + kk;
+        double fr[BR + 1];
+#pragma unroll
+        for (int t = 0; t <= BR; ++t) fr[t] = (beta_f2d(tb[8 * t]) * ek[t]) * sc;
+        const double fa = (beta_f2d(tb[8 * BR]) * ekb) * sc;   // == fr[BR] bit for bit
+        if (v < n && kok) {
+            const double ph = fa * wv2[v];
+            rs += ph;
+            if (!STM_DBG_NO_PHI) red_add_f64(ssb + (size_t)wid[v] * TS, ph);
+        }
+#pragma unroll
+        for (int t = 0; t <= BR; ++t)
+            asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                         : "+d"(acc[t][0]), "+d"(acc[t][1])
+                         : "d"(fa), "d"(fr[t]));
+    }
+}
+
 template <int KPL>
 __global__ void __launch_bounds__(STM_POST_MAX_THREADS, 1) post_group_kernel(const EstepParams P) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    const int grp = threadIdx.x / POST_GT;
-    const int gt = threadIdx.x - grp * POST_GT;
-    const int wg = gt >> 5, lane = gt & 31;
+    // warp-uniform indices go through redux.sync so that the compiler KNOWS they are uniform (no
+    // reconvergence scaffolding around the warp-synchronous instructions they guard)
+    const int warp_u = __reduce_max_sync(STM_FULL, (int)(threadIdx.x >> 5));
+    const int grp = warp_u / POST_GW;
+    const int wg = warp_u - grp * POST_GW;
+    const int lane = threadIdx.x & 31;
+    const int gt = wg * 32 + lane;
     const int K = P.K, K1 = K - 1, TS = P.TS;
     constexpr int KV = KPL * 32;
     constexpr int KVS = KV + 8;
@@ -1661,10 +1696,10 @@ __global__ void __launch_bounds__(STM_POST_MAX_THREADS, 1) post_group_kernel(con
     tile_bytes = (tile_bytes + 127) & ~(size_t)127;
     float* tile = reinterpret_cast<float*>(base);
     double* Hm = reinterpret_cast<double*>(base);   // aliases the tile once it is dead
-    size_t w_bytes = (size_t)P.n_cap * 16;
+    size_t w_bytes = (size_t)(P.n_cap + 4) * 16;
     if (w_bytes < (size_t)4 * POST_UST * 8) w_bytes = (size_t)4 * POST_UST * 8;
-    double* wv = reinterpret_cast<double*>(base + tile_bytes);   // [n_cap] sqrt(c_v)/colsum_v
-    double* wv2 = wv + P.n_cap;                                  // [n_cap] sqrt(c_v)
+    double* wv = reinterpret_cast<double*>(base + tile_bytes);   // [n_cap + 4] sqrt(c_v)/colsum_v, zero past n
+    double* wv2 = wv + P.n_cap + 4;                              // [n_cap + 4] sqrt(c_v)
     double* Dg = wv;                      // the dense phase re-uses the per-word block:
     double* ubuf = wv + POST_UST;         //   diagonal, 2 pivot vectors, pivots
     double* dvec = wv + 3 * POST_UST;
@@ -1707,11 +1742,11 @@ __global__ void __launch_bounds__(STM_POST_MAX_THREADS, 1) post_group_kernel(con
         if (gt == 0) *qslot = (int)atomicAdd(P.queue, 1u);
         fence_proxy_async();   // the previous document's generic smem accesses precede the async writes
         group_bar(grp);
-        const int qi = *qslot;
+        const int qi = __reduce_max_sync(STM_FULL, *qslot);
         if (qi >= P.n_docs) break;
         const int d = P.docs[qi];
         const long long p0 = P.doc_ptr[d];
-        const int n = (int)(P.doc_ptr[d + 1] - p0);
+        const int n = __reduce_max_sync(STM_FULL, (int)(P.doc_ptr[d + 1] - p0));
         const int asp = P.aspect ? P.aspect[d] : 0;
         const float* beta_a = P.beta_t + (size_t)asp * P.V * TS;
         double* beta_ss_a = P.beta_ss_t + (size_t)asp * P.V * TS;
@@ -1797,6 +1832,7 @@ __global__ void __launch_bounds__(STM_POST_MAX_THREADS, 1) post_group_kernel(con
                 wv[v] = sq / (s0 + s1);   // sqrt(c_v)/colsum_v
                 wv2[v] = sq;
             }
+            if (gt < 4) wv[n + gt] = 0.0;
             loglik = group_sum(logprod_value(lp), red, wg, lane, grp);   // also publishes wv / wv2
         }
 
@@ -1822,50 +1858,20 @@ __global__ void __launch_bounds__(STM_POST_MAX_THREADS, 1) post_group_kernel(con
                 const double ekb = v0[kb];
                 const bool kok = kb < K;
                 double* ssb = beta_ss_a + kb;
-#define STM_FR(t) fr[t] = (beta_f2d(tb[8 * (t)]) * ek[t]) * sc;
-#define STM_MMA(t)                                                                               \
-    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" \
-                 : "+d"(acc[t][0]), "+d"(acc[t][1])                                              \
-                 : "d"(fa), "d"(fr[t]));
-#pragma unroll 1
-                for (int vb = 0; vb < n; vb += 4) {
-                    const int v = vb + w4;
-                    const bool vok = v < n;
-                    const int vc = vok ? v : 0;
-                    const double sc = vok ? wv[vc] : 0.0;
-                    const float* tb = tile + (size_t)vc * TS + kk;
-                    double fr[NBMAX];
-                    // fr[t] for t <= br (fall-through: no per-block guards; reads past the row end hit the
-                    // next row / the zeroed spare row and are multiplied by ek = 0)
-                    switch (br) {
-                        case 7: if (NBMAX > 7) { STM_FR(NBMAX > 7 ? 7 : 0) }
-                        case 6: if (NBMAX > 6) { STM_FR(NBMAX > 6 ? 6 : 0) }
-                        case 5: if (NBMAX > 5) { STM_FR(NBMAX > 5 ? 5 : 0) }
-                        case 4: if (NBMAX > 4) { STM_FR(NBMAX > 4 ? 4 : 0) }
-                        case 3: STM_FR(3)
-                        case 2: STM_FR(2)
-                        case 1: STM_FR(1)
-                        default: STM_FR(0)
-                    }
-                    const double fa = (beta_f2d(tb[8 * br]) * ekb) * sc;
-                    if (vok && kok) {
-                        const double ph = fa * wv2[vc];
-                        rs += ph;
-                        if (!STM_DBG_NO_PHI) red_add_f64(ssb + (size_t)wid[vc] * TS, ph);
-                    }
-                    switch (br) {
-                        case 7: if (NBMAX > 7) { STM_MMA(NBMAX > 7 ? 7 : 0) }
-                        case 6: if (NBMAX > 6) { STM_MMA(NBMAX > 6 ? 6 : 0) }
-                        case 5: if (NBMAX > 5) { STM_MMA(NBMAX > 5 ? 5 : 0) }
-                        case 4: if (NBMAX > 4) { STM_MMA(NBMAX > 4 ? 4 : 0) }
-                        case 3: STM_MMA(3)
-                        case 2: STM_MMA(2)
-                        case 1: STM_MMA(1)
-                        default: STM_MMA(0)
-                    }
+                switch (br) {
+                    case 0: hess_row_pass<NBMAX, 0>(tile, TS, n, wv, wv2, wid, ek, ekb, kok, ssb, w4, kk, acc, rs); break;
+                    case 1: hess_row_pass<NBMAX, 1>(tile, TS, n, wv, wv2, wid, ek, ekb, kok, ssb, w4, kk, acc, rs); break;
+                    case 2: hess_row_pass<NBMAX, 2>(tile, TS, n, wv, wv2, wid, ek, ekb, kok, ssb, w4, kk, acc, rs); break;
+                    case 3: hess_row_pass<NBMAX, 3>(tile, TS, n, wv, wv2, wid, ek, ekb, kok, ssb, w4, kk, acc, rs); break;
+                    default:
+                        if constexpr (NBMAX > 4) {
+                            if (br == 4) hess_row_pass<NBMAX, 4>(tile, TS, n, wv, wv2, wid, ek, ekb, kok, ssb, w4, kk, acc, rs);
+                            else if (br == 5) hess_row_pass<NBMAX, 5>(tile, TS, n, wv, wv2, wid, ek, ekb, kok, ssb, w4, kk, acc, rs);
+                            else if (br == 6) hess_row_pass<NBMAX, 6>(tile, TS, n, wv, wv2, wid, ek, ekb, kok, ssb, w4, kk, acc, rs);
+                            else hess_row_pass<NBMAX, 7>(tile, TS, n, wv, wv2, wid, ek, ekb, kok, ssb, w4, kk, acc, rs);
+                        }
+                        break;
                 }
-#undef STM_FR
-#undef STM_MMA
                 // C fragment: row = lane>>2, cols = 2*(lane&3) + {0,1}
                 const int gi = br * 8 + kk;
 #pragma unroll

@@ -138,7 +138,7 @@ size_t post_group_smem(int n_cap, int TS, int K1, int KPL) {
     const size_t hb = (size_t)K1 * HS * 8;
     if (hb > tile) tile = hb;
     tile = (tile + 127) & ~(size_t)127;
-    size_t wb = (size_t)n_cap * 16;
+    size_t wb = (size_t)(n_cap + 4) * 16;
     if (wb < (size_t)4 * stm::POST_UST * 8) wb = (size_t)4 * stm::POST_UST * 8;
     const int KVS = KPL * 32 + 8;
     const size_t total = tile + wb + (size_t)4 * KVS * 8 + 64 + (size_t)n_cap * 4 + (size_t)((n_cap + 1) & ~1) * 4 + 16;
