@@ -51,6 +51,10 @@ int stm_beta_stride(int K);
 /* number of this library's own kernel launches issued so far on this context (bench.py's
  * gpu_launches; cuBLAS/cuSOLVER kernels are not counted) */
 int64_t stm_launch_count(const stm_ctx* ctx);
+/* durations (ms, CUDA events on the stream stm_estep was given) of the two kernel phases of the LAST
+ * stm_estep call: ms2[0] = kernel A (per-document BFGS, stm.py:536-545 + SciPy), ms2[1] = kernel B
+ * (theta, phi, Hessian, Cholesky pivots, bound, nu; stm.py:546-590).  Blocks until that call is done. */
+int stm_estep_kernel_ms(stm_ctx* ctx, double* ms2);
 
 /* ---- corpus ------------------------------------------------------------------------------------ */
 

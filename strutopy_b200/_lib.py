@@ -14,7 +14,7 @@ STM_ERR_INVALID, STM_ERR_CUDA, STM_ERR_NOT_PD, STM_ERR_UNSUPPORTED, STM_ERR_NO_C
 MODEL_STM, MODEL_CTM = 0, 1
 
 EXPORTS = [
-    "stm_create", "stm_destroy", "stm_last_error", "stm_beta_stride", "stm_launch_count",
+    "stm_create", "stm_destroy", "stm_last_error", "stm_beta_stride", "stm_launch_count", "stm_estep_kernel_ms",
     "stm_set_corpus", "stm_stats_layout", "stm_prologue", "stm_estep", "stm_moments", "stm_mstep",
     "stm_beta_to_wordmajor", "stm_wordmajor_to_kv", "stm_estep_host",
 ]
@@ -47,6 +47,7 @@ def load():
     L.stm_beta_stride.argtypes = [i32]
     L.stm_launch_count.argtypes = [vp]
     L.stm_launch_count.restype = i64
+    L.stm_estep_kernel_ms.argtypes = [vp, C.POINTER(C.c_double)]
     L.stm_set_corpus.argtypes = [vp, i64, vp, vp, vp, vp]
     L.stm_stats_layout.argtypes = [vp, i32, C.POINTER(i64)]
     L.stm_prologue.argtypes = [vp, vp, vp, vp, vp]
@@ -123,6 +124,12 @@ class Context:
 
     def launch_count(self):
         return int(load().stm_launch_count(self._h))
+
+    def estep_kernel_ms(self):
+        """(kernel A ms, kernel B ms) of the last E-step on this context (CUDA events on its stream)."""
+        ms = (C.c_double * 2)()
+        check(self._h, load().stm_estep_kernel_ms(self._h, ms))
+        return float(ms[0]), float(ms[1])
 
     def estep_host(self, beta, mu, siginv, sigmaentropy, eta, want_docs=True):
         """E_step() with host fp64 arrays in the reference's layout (stm.py:489-597)."""

@@ -71,6 +71,7 @@ struct stm_ctx {
     cublasHandle_t cublas = nullptr;
     cusolverDnHandle_t cusolver = nullptr;
     int64_t launches = 0;
+    cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};   // E-step phases: before kernel A, between, after kernel B
     std::string err;
 };
 
@@ -449,6 +450,17 @@ const char* stm_last_error(const stm_ctx* ctx) { return ctx ? ctx->err.c_str() :
 
 int64_t stm_launch_count(const stm_ctx* ctx) { return ctx ? ctx->launches : 0; }
 
+int stm_estep_kernel_ms(stm_ctx* ctx, double* ms2) {
+    if (!ctx || !ms2) return STM_ERR_INVALID;
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaEventSynchronize(ctx->ev[2]));
+    float a = 0.f, b = 0.f;
+    CU(cudaEventElapsedTime(&a, ctx->ev[0], ctx->ev[1]));
+    CU(cudaEventElapsedTime(&b, ctx->ev[1], ctx->ev[2]));
+    ms2[0] = a; ms2[1] = b;
+    return STM_OK;
+}
+
 int stm_create(int device, int K, int V, int A, stm_ctx** out) {
     stm_ctx* ctx = nullptr;
     if (!out) return fail(ctx, STM_ERR_INVALID, "out is NULL");
@@ -488,6 +500,7 @@ int stm_create(int device, int K, int V, int A, stm_ctx** out) {
     cusolverDnDpotrf_bufferSize(c->cusolver, CUBLAS_FILL_MODE_LOWER, c->K1, c->d_msmall, c->K1, &c->potrf_lwork);
     if (c->potrf_lwork < 1) c->potrf_lwork = 1;
     cudaMalloc(&c->d_potrf_work, sizeof(double) * c->potrf_lwork);
+    for (int i = 0; i < 3; ++i) cudaEventCreate(&c->ev[i]);
     *out = c;
     return STM_OK;
 }
@@ -499,6 +512,7 @@ void stm_destroy(stm_ctx* c) {
     cudaFree(c->d_msmall); cudaFree(c->d_info); cudaFree(c->d_potrf_work); cudaFree(c->d_syevd_work);
     if (c->cublas) cublasDestroy(c->cublas);
     if (c->cusolver) cusolverDnDestroy(c->cusolver);
+    for (int i = 0; i < 3; ++i) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
     delete c;
 }
 
@@ -672,39 +686,46 @@ int stm_estep(stm_ctx* ctx, const float* beta_t_dev, const double* mu_dev, const
     CU(cudaMemsetAsync(stats_dev + off[0], 0, sizeof(double) * (size_t)ctx->A * ctx->V * ctx->TS, st));
     CU(cudaMemsetAsync(ctx->d_sigma_rep, 0, sizeof(double) * ctx->n_rep * K1 * K1, st));
     CU(cudaMemsetAsync(ctx->d_queues, 0, sizeof(unsigned int) * 32, st));
-    int ci = 0;
-    for (const auto& lc : ctx->classes) {
-        stm::EstepParams P;
-        P.doc_ptr = ctx->d_doc_ptr; P.word_id = ctx->d_word_id; P.count = ctx->d_count; P.aspect = ctx->d_aspect;
-        P.docs = lc.d_docs; P.n_docs = lc.n_docs; P.queue = ctx->d_queues + ci;
-        P.K = ctx->K; P.V = ctx->V; P.A = ctx->A; P.TS = ctx->TS;
-        P.beta_t = beta_t_dev; P.mu = mu_dev; P.prior = prior_dev;
-        P.eta = eta_dev; P.theta = theta_dev; P.doc_bound = doc_bound_dev; P.doc_info = doc_info_dev;
-        P.doc_nfev = doc_nfev_dev;
-        P.beta_ss_t = stats_dev + off[0];
-        P.sigma_ss_rep = ctx->d_sigma_rep; P.n_rep = ctx->n_rep;
-        P.scratch = ctx->d_scratch; P.scratch_stride = ctx->scratch_stride;
-        P.n_cap = lc.n_cap; P.smem_per_warp = lc.smem_per_warp;
-        P.smem_small = lc.smem_small; P.tm_warps = lc.tm_warps; P.tm_cols = lc.tm_cols;
-        P.dbg_cycles = ctx->d_dbg;
-        static const int dev_skip = getenv("STM_DEV_SKIP") ? atoi(getenv("STM_DEV_SKIP")) : 0;  // 1: no kernel A, 2: no kernel B (timing only)
-        if (dev_skip != 1)
-            CU(launch_bfgs(ctx->KPL, P, lc.J, lc.grid, lc.warps * 32, (size_t)lc.smem_small * lc.warps + (size_t)lc.smem_per_warp * (lc.warps - lc.tm_warps), st));
-        P.queue = ctx->d_queues + 16 + ci;
-        P.smem_per_warp = lc.post_smem_per_warp;
-        if (dev_skip != 2) {
-            if (lc.post_groups > 0) {
-                const size_t smem = (size_t)lc.post_smem_per_warp * lc.post_groups;
-                const int block = lc.post_groups * stm::POST_GT;
-                CU(ctx->KPL == 1 ? stm_launch_post_group_kpl1(P, lc.post_grid, block, smem, st)
-                                 : stm_launch_post_group_kpl2(P, lc.post_grid, block, smem, st));
-            } else {
-                CU(launch_post(ctx->KPL, P, lc.post_grid, lc.post_warps * 32,
-                               (size_t)lc.post_smem_per_warp * lc.post_warps, st));
+    static const int dev_skip = getenv("STM_DEV_SKIP") ? atoi(getenv("STM_DEV_SKIP")) : 0;  // 1: no kernel A, 2: no kernel B (timing only)
+    // kernel A (BFGS) for every length class, then kernel B (post-optimisation) for every length class;
+    // three events bracket the two phases (stm_estep_kernel_ms)
+    CU(cudaEventRecord(ctx->ev[0], st));
+    for (int phase = 0; phase < 2; ++phase) {
+        int ci = 0;
+        for (const auto& lc : ctx->classes) {
+            stm::EstepParams P;
+            P.doc_ptr = ctx->d_doc_ptr; P.word_id = ctx->d_word_id; P.count = ctx->d_count; P.aspect = ctx->d_aspect;
+            P.docs = lc.d_docs; P.n_docs = lc.n_docs; P.queue = ctx->d_queues + 16 * phase + ci;
+            P.K = ctx->K; P.V = ctx->V; P.A = ctx->A; P.TS = ctx->TS;
+            P.beta_t = beta_t_dev; P.mu = mu_dev; P.prior = prior_dev;
+            P.eta = eta_dev; P.theta = theta_dev; P.doc_bound = doc_bound_dev; P.doc_info = doc_info_dev;
+            P.doc_nfev = doc_nfev_dev;
+            P.beta_ss_t = stats_dev + off[0];
+            P.sigma_ss_rep = ctx->d_sigma_rep; P.n_rep = ctx->n_rep;
+            P.scratch = ctx->d_scratch; P.scratch_stride = ctx->scratch_stride;
+            P.n_cap = lc.n_cap; P.smem_per_warp = lc.smem_per_warp;
+            P.smem_small = lc.smem_small; P.tm_warps = lc.tm_warps; P.tm_cols = lc.tm_cols;
+            P.dbg_cycles = ctx->d_dbg;
+            if (phase == 0) {
+                if (dev_skip != 1)
+                    CU(launch_bfgs(ctx->KPL, P, lc.J, lc.grid, lc.warps * 32,
+                                   (size_t)lc.smem_small * lc.warps + (size_t)lc.smem_per_warp * (lc.warps - lc.tm_warps), st));
+            } else if (dev_skip != 2) {
+                P.smem_per_warp = lc.post_smem_per_warp;
+                if (lc.post_groups > 0) {
+                    const size_t smem = (size_t)lc.post_smem_per_warp * lc.post_groups;
+                    const int block = lc.post_groups * stm::POST_GT;
+                    CU(ctx->KPL == 1 ? stm_launch_post_group_kpl1(P, lc.post_grid, block, smem, st)
+                                     : stm_launch_post_group_kpl2(P, lc.post_grid, block, smem, st));
+                } else {
+                    CU(launch_post(ctx->KPL, P, lc.post_grid, lc.post_warps * 32,
+                                   (size_t)lc.post_smem_per_warp * lc.post_warps, st));
+                }
             }
+            ctx->launches++;
+            ci++;
         }
-        ctx->launches += 2;
-        ci++;
+        CU(cudaEventRecord(ctx->ev[phase + 1], st));
     }
     estep_epilogue_kernel<<<1, 1024, 0, st>>>(ctx->d_sigma_rep, ctx->n_rep, K1, doc_bound_dev, ctx->D,
                                               stats_dev + off[1], stats_dev + off[2], stats_dev + off[3]);
