@@ -61,7 +61,8 @@ def main():
         nf = d['nfev']
         out.append(f"      nfev pct50/90/99/99.9/max {np.percentile(nf,50):.0f}/{np.percentile(nf,90):.0f}/{np.percentile(nf,99):.0f}/"
                    f"{np.percentile(nf,99.9):.0f}/{nf.max()}  nit max {d['nit'].max()}  sum nfev {nf.sum()}  status {np.bincount(d['status'])}")
-        out.append(f"it{it}: estep {e0.elapsed_time(e1):7.2f} ms  nfev {d['nfev'].mean():5.1f}  nit {d['nit'].mean():4.2f} "
+        ka, kb = m._ctx.estep_kernel_ms()
+        out.append(f"it{it}: estep {e0.elapsed_time(e1):7.2f} ms (A {ka:6.2f} + B {kb:5.2f})  nfev {d['nfev'].mean():5.1f}  nit {d['nit'].mean():4.2f} "
                    f"repair {np.mean(d['repair'] > 0):.2f}  mstep {tm*1e3:5.2f} ms  bound {b:.6f}")
     print(f"== {a.tag}")
     print("\n".join(out), flush=True)
