@@ -132,6 +132,21 @@ int stm_estep_host(stm_ctx* ctx, const double* beta, const double* mu, const dou
                    double* sigma_ss, double* bound, double* doc_bound, int32_t* doc_status,
                    int32_t* doc_nit, int32_t* doc_repair);
 
+/* ---- held-out likelihood, document completion ---------------------------------
+ * Replaces eval_heldout(heldout, theta, beta), /root/reference/src/modules/heldout.py:88-97:
+ *   doc_ll[d] = sum_w c_w log(theta_d . beta[:, w]) / sum_w c_w   over the held-out words of d,
+ *   mean = np.mean(doc_ll)  (an empty held-out document gives NaN, as in the reference).
+ * stm_heldout: device pointers, the fit's own buffers (held-out CSR, theta double [D][K], word-major
+ * float beta [V][TS]); asynchronous on `stream`; doc_ll_dev [D] and mean_dev [1] are outputs.
+ * stm_heldout_host: HOST pointers in the reference's layouts (theta double [D][K], beta double
+ * [K][V], kept in fp64 on the device); doc_ll may be NULL; blocks until done.  A = 1 only. */
+int stm_heldout(stm_ctx* ctx, int64_t D, const int64_t* doc_ptr_dev, const int32_t* word_id_dev,
+                const float* count_dev, const double* theta_dev, const float* beta_t_dev,
+                double* doc_ll_dev, double* mean_dev, void* stream);
+int stm_heldout_host(stm_ctx* ctx, int64_t D, const int64_t* doc_ptr, const int32_t* word_id,
+                     const float* count, const double* theta, const double* beta_kv, double* doc_ll,
+                     double* mean);
+
 #ifdef __cplusplus
 }
 #endif

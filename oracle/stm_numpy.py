@@ -232,3 +232,20 @@ def em(doc_ptr, word_id, count, beta0, X, n_iter, model="STM", mode="ols", sigpr
         if it == n_iter - 1:
             break
     return dict(beta=beta, theta=theta, eta=eta, mu=mu, sigma=sigma, gamma=gamma, bounds=bounds)
+
+
+def eval_heldout(doc_ptr, word_id, count, theta, beta, return_doc_ll=False):
+    """Held-out likelihood by document completion, restating eval_heldout of
+    /root/reference/src/modules/heldout.py:88-97 on CSR arrays: document i is scored with theta[i];
+    per-document value = sum_w c_w log(theta_i @ beta[:, w]) / sum_w c_w; result = np.mean over documents."""
+    D = len(doc_ptr) - 1
+    doc_ll = np.empty(D, dtype=np.float64)
+    for i in range(D):
+        lo, hi = int(doc_ptr[i]), int(doc_ptr[i + 1])
+        w = np.asarray(word_id[lo:hi], dtype=np.intp)
+        c = np.asarray(count[lo:hi], dtype=np.float64)
+        word_ll = [c[j] * np.log(theta[i] @ beta[:, w[j]]) for j in range(hi - lo)]
+        with np.errstate(invalid="ignore", divide="ignore"):
+            doc_ll[i] = np.sum(word_ll) / np.sum(c)
+    mean = np.mean(doc_ll)
+    return (mean, doc_ll) if return_doc_ll else mean

@@ -4,6 +4,7 @@
 (include/stm_b200.h); no CPU fallback."""
 from . import _lib  # noqa: F401
 from .corpus import pack_corpus  # noqa: F401
+from .heldout import cut_in_half, eval_heldout, split_corpus  # noqa: F401
 from .stm import STM  # noqa: F401
 
-__all__ = ["STM", "pack_corpus"]
+__all__ = ["STM", "pack_corpus", "eval_heldout", "cut_in_half", "split_corpus"]

@@ -16,7 +16,7 @@ MODEL_STM, MODEL_CTM = 0, 1
 EXPORTS = [
     "stm_create", "stm_destroy", "stm_last_error", "stm_beta_stride", "stm_launch_count", "stm_estep_kernel_ms",
     "stm_set_corpus", "stm_stats_layout", "stm_prologue", "stm_estep", "stm_moments", "stm_mstep",
-    "stm_beta_to_wordmajor", "stm_wordmajor_to_kv", "stm_estep_host",
+    "stm_beta_to_wordmajor", "stm_wordmajor_to_kv", "stm_estep_host", "stm_heldout", "stm_heldout_host",
 ]
 
 _lib = None
@@ -48,6 +48,8 @@ def load():
     L.stm_launch_count.argtypes = [vp]
     L.stm_launch_count.restype = i64
     L.stm_estep_kernel_ms.argtypes = [vp, C.POINTER(C.c_double)]
+    L.stm_heldout.argtypes = [vp, i64, vp, vp, vp, vp, vp, vp, vp, vp]
+    L.stm_heldout_host.argtypes = [vp, i64, vp, vp, vp, vp, vp, vp, C.POINTER(C.c_double)]
     L.stm_set_corpus.argtypes = [vp, i64, vp, vp, vp, vp]
     L.stm_stats_layout.argtypes = [vp, i32, C.POINTER(i64)]
     L.stm_prologue.argtypes = [vp, vp, vp, vp, vp]
@@ -124,6 +126,22 @@ class Context:
 
     def launch_count(self):
         return int(load().stm_launch_count(self._h))
+
+    def heldout_host(self, doc_ptr, word_id, count, theta, beta):
+        """eval_heldout (heldout.py:88-97) with host arrays -> (mean, per-document per-word log-likelihood)"""
+        doc_ptr = np.ascontiguousarray(doc_ptr, dtype=np.int64)
+        word_id = np.ascontiguousarray(word_id, dtype=np.int32)
+        count = np.ascontiguousarray(count, dtype=np.float32)
+        D = doc_ptr.shape[0] - 1
+        theta = np.ascontiguousarray(theta, dtype=np.float64)
+        beta = np.ascontiguousarray(beta, dtype=np.float64)
+        if theta.shape != (D, self.K) or beta.shape != (self.K, self.V):
+            raise ValueError(f"theta must be ({D}, {self.K}) and beta ({self.K}, {self.V})")
+        doc_ll = np.empty(D, dtype=np.float64)
+        mean = C.c_double()
+        check(self._h, load().stm_heldout_host(self._h, D, hp(doc_ptr), hp(word_id), hp(count), hp(theta), hp(beta),
+                                               hp(doc_ll), C.byref(mean)))
+        return float(mean.value), doc_ll
 
     def estep_kernel_ms(self):
         """(kernel A ms, kernel B ms) of the last E-step on this context (CUDA events on its stream)."""

@@ -442,6 +442,76 @@ void free_corpus(stm_ctx* c) {
 // =================================================================================================
 // C ABI
 // =================================================================================================
+// ---- held-out likelihood (document completion), /root/reference/src/modules/heldout.py:88-97 ------------
+// doc_ll[d] = sum_w c_w log(theta_d . beta[:, w]) / sum_w c_w over the held-out words of document d; one warp per
+// document, lane <-> word, theta_d broadcast from shared memory, beta word-major (one contiguous row per word).
+template <typename BT>
+__global__ void heldout_kernel(const long long* __restrict__ doc_ptr, const int* __restrict__ word_id,
+                               const float* __restrict__ count, const double* __restrict__ theta,
+                               const BT* __restrict__ beta_t, int K, int TS, long long D, double* __restrict__ doc_ll) {
+    extern __shared__ double th_s[];   // [warps][K]
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    double* th = th_s + (size_t)warp * K;
+    for (long long d = (long long)blockIdx.x * nw + warp; d < D; d += (long long)gridDim.x * nw) {
+        __syncwarp();
+        for (int k = lane; k < K; k += 32) th[k] = theta[(size_t)d * K + k];
+        __syncwarp();
+        const long long p0 = doc_ptr[d], p1 = doc_ptr[d + 1];
+        double ll = 0.0, nsum = 0.0;
+        for (long long p = p0 + lane; p < p1; p += 32) {
+            const BT* row = beta_t + (size_t)word_id[p] * TS;
+            double s = 0.0;
+            for (int k = 0; k < K; ++k) s = fma(th[k], (double)row[k], s);
+            const double c = (double)count[p];
+            ll += c * log(s);
+            nsum += c;
+        }
+        for (int o = 16; o > 0; o >>= 1) {
+            ll += __shfl_xor_sync(0xffffffffu, ll, o);
+            nsum += __shfl_xor_sync(0xffffffffu, nsum, o);
+        }
+        if (lane == 0) doc_ll[d] = ll / nsum;   // an empty document gives 0/0 = NaN, like the reference
+    }
+}
+// np.mean(doc_ll): fixed-order tree sum in one block (deterministic)
+__global__ void mean_kernel(const double* __restrict__ x, long long n, double* __restrict__ out) {
+    __shared__ double sh[1024];
+    double a = 0.0;
+    for (long long i = threadIdx.x; i < n; i += blockDim.x) a += x[i];
+    sh[threadIdx.x] = a;
+    __syncthreads();
+    for (int o = blockDim.x >> 1; o > 0; o >>= 1) {
+        if ((int)threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *out = sh[0] / (double)n;
+}
+__global__ void beta_kv_to_wordmajor_f64_kernel(const double* __restrict__ src, double* __restrict__ dst, int K, int V,
+                                                int TS) {
+    const long long total = (long long)V * TS;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        const int k = (int)(i % TS);
+        const long long v = i / TS;
+        dst[i] = (k < K) ? src[(size_t)k * V + v] : 0.0;
+    }
+}
+
+template <typename BT>
+int heldout_launch(stm_ctx* ctx, int64_t D, const int64_t* doc_ptr_dev, const int32_t* word_id_dev,
+                   const float* count_dev, const double* theta_dev, const BT* beta_t_dev, double* doc_ll_dev,
+                   double* mean_dev, cudaStream_t st) {
+    const int warps = 8;
+    const int grid = (int)std::min<int64_t>((D + warps - 1) / warps, (int64_t)ctx->sm_count * 8);
+    heldout_kernel<BT><<<std::max(grid, 1), warps * 32, sizeof(double) * warps * ctx->K, st>>>(
+        reinterpret_cast<const long long*>(doc_ptr_dev), word_id_dev, count_dev, theta_dev, beta_t_dev, ctx->K, ctx->TS,
+        (long long)D, doc_ll_dev);
+    mean_kernel<<<1, 1024, 0, st>>>(doc_ll_dev, (long long)D, mean_dev);
+    ctx->launches += 2;
+    CU(cudaGetLastError());
+    return STM_OK;
+}
+
 extern "C" {
 
 int stm_beta_stride(int K) { return beta_stride(K); }
@@ -940,6 +1010,75 @@ int stm_estep_host(stm_ctx* ctx, const double* beta, const double* mu, const dou
     }
     CU(cudaStreamSynchronize(st));
     return STM_OK;
+}
+
+int stm_heldout(stm_ctx* ctx, int64_t D, const int64_t* doc_ptr_dev, const int32_t* word_id_dev,
+                const float* count_dev, const double* theta_dev, const float* beta_t_dev, double* doc_ll_dev,
+                double* mean_dev, void* stream) {
+    if (!ctx) return STM_ERR_INVALID;
+    if (D < 1 || !doc_ptr_dev || !word_id_dev || !count_dev || !theta_dev || !beta_t_dev || !doc_ll_dev || !mean_dev)
+        return fail(ctx, STM_ERR_INVALID, "stm_heldout: NULL pointer or no documents");
+    if (ctx->A != 1) return fail(ctx, STM_ERR_UNSUPPORTED, "stm_heldout: eval_heldout takes one K x V beta (A = 1)");
+    CU(cudaSetDevice(ctx->device));
+    return heldout_launch<float>(ctx, D, doc_ptr_dev, word_id_dev, count_dev, theta_dev, beta_t_dev, doc_ll_dev,
+                                 mean_dev, (cudaStream_t)stream);
+}
+
+int stm_heldout_host(stm_ctx* ctx, int64_t D, const int64_t* doc_ptr, const int32_t* word_id, const float* count,
+                     const double* theta, const double* beta_kv, double* doc_ll, double* mean) {
+    if (!ctx) return STM_ERR_INVALID;
+    if (D < 1 || !doc_ptr || !theta || !beta_kv || !mean)
+        return fail(ctx, STM_ERR_INVALID, "stm_heldout_host: NULL pointer or no documents");
+    if (ctx->A != 1) return fail(ctx, STM_ERR_UNSUPPORTED, "stm_heldout_host: eval_heldout takes one K x V beta (A = 1)");
+    const int64_t nnz = doc_ptr[D];
+    if (doc_ptr[0] != 0 || nnz < 0 || (nnz > 0 && (!word_id || !count)))
+        return fail(ctx, STM_ERR_INVALID, "stm_heldout_host: bad CSR arrays");
+    for (int64_t d = 0; d < D; ++d)
+        if (doc_ptr[d + 1] < doc_ptr[d]) return fail(ctx, STM_ERR_INVALID, "doc_ptr must be non-decreasing");
+    for (int64_t i = 0; i < nnz; ++i)
+        if (word_id[i] < 0 || word_id[i] >= ctx->V) return fail(ctx, STM_ERR_INVALID, "word id out of range [0, V)");
+    CU(cudaSetDevice(ctx->device));
+    const int K = ctx->K, V = ctx->V, TS = ctx->TS;
+    long long* d_ptr = nullptr; int* d_ids = nullptr; float* d_cnt = nullptr;
+    double *d_theta = nullptr, *d_bkv = nullptr, *d_bt = nullptr, *d_ll = nullptr;
+    int rc = STM_OK;
+    auto cleanup = [&]() {
+        cudaFree(d_ptr); cudaFree(d_ids); cudaFree(d_cnt); cudaFree(d_theta); cudaFree(d_bkv); cudaFree(d_bt); cudaFree(d_ll);
+    };
+#define HCU(call)                                                                                    \
+    do {                                                                                             \
+        cudaError_t e_ = (call);                                                                     \
+        if (e_ != cudaSuccess) {                                                                     \
+            cleanup();                                                                               \
+            return fail(ctx, STM_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_));      \
+        }                                                                                            \
+    } while (0)
+    HCU(cudaMalloc(&d_ptr, sizeof(long long) * (D + 1)));
+    HCU(cudaMalloc(&d_ids, sizeof(int) * std::max<int64_t>(nnz, 1)));
+    HCU(cudaMalloc(&d_cnt, sizeof(float) * std::max<int64_t>(nnz, 1)));
+    HCU(cudaMalloc(&d_theta, sizeof(double) * D * K));
+    HCU(cudaMalloc(&d_bkv, sizeof(double) * (size_t)K * V));
+    HCU(cudaMalloc(&d_bt, sizeof(double) * (size_t)V * TS));
+    HCU(cudaMalloc(&d_ll, sizeof(double) * (D + 1)));
+    HCU(cudaMemcpy(d_ptr, doc_ptr, sizeof(long long) * (D + 1), cudaMemcpyHostToDevice));
+    if (nnz) {
+        HCU(cudaMemcpy(d_ids, word_id, sizeof(int) * nnz, cudaMemcpyHostToDevice));
+        HCU(cudaMemcpy(d_cnt, count, sizeof(float) * nnz, cudaMemcpyHostToDevice));
+    }
+    HCU(cudaMemcpy(d_theta, theta, sizeof(double) * D * K, cudaMemcpyHostToDevice));
+    HCU(cudaMemcpy(d_bkv, beta_kv, sizeof(double) * (size_t)K * V, cudaMemcpyHostToDevice));
+    beta_kv_to_wordmajor_f64_kernel<<<ctx->sm_count * 4, 256>>>(d_bkv, d_bt, K, V, TS);
+    ctx->launches++;
+    // the host entry keeps beta in fp64 (reference arithmetic); the device entry uses the fit's fp32 beta
+    rc = heldout_launch<double>(ctx, D, reinterpret_cast<const int64_t*>(d_ptr), d_ids, d_cnt, d_theta, d_bt, d_ll,
+                                d_ll + D, nullptr);
+    if (rc == STM_OK) {
+        HCU(cudaMemcpy(mean, d_ll + D, sizeof(double), cudaMemcpyDeviceToHost));
+        if (doc_ll) HCU(cudaMemcpy(doc_ll, d_ll, sizeof(double) * D, cudaMemcpyDeviceToHost));
+    }
+#undef HCU
+    cleanup();
+    return rc;
 }
 
 }  // extern "C"

@@ -421,6 +421,29 @@ class STM:
     # ------------------------------------------------------------------------------------------------
     # persistence / inspection — stm.py:1120-1259 (host, unchanged formats)
     # ------------------------------------------------------------------------------------------------
+    def eval_heldout(self, heldout, return_doc_ll=False):
+        """Held-out likelihood of the fitted model by document completion (heldout.py:88-97; the evaluate step of
+        05_train.py:99-122) on the device-resident theta and beta: heldout[i] is scored with theta[i]."""
+        torch = self._torch
+        if self._use_aspect:
+            raise NotImplementedError("eval_heldout takes one K x V beta (no content covariate), heldout.py:88-97")
+        ptr, ids, cnt = pack_corpus(list(heldout) if not isinstance(heldout, tuple) else heldout)
+        D = ptr.shape[0] - 1
+        if D < 1 or D > self.N_local:
+            raise ValueError("held-out documents must be 1..N (document i is scored with theta[i])")
+        if ids.size and (ids.min() < 0 or ids.max() >= self.V):
+            raise IndexError("word id out of range [0, V)")
+        dev = self._dev
+        d_ptr = torch.from_numpy(ptr).to(dev)
+        d_ids = torch.from_numpy(ids).to(dev) if ids.size else torch.zeros(1, dtype=torch.int32, device=dev)
+        d_cnt = torch.from_numpy(cnt).to(dev) if cnt.size else torch.zeros(1, dtype=torch.float32, device=dev)
+        out = torch.empty(D + 1, dtype=torch.float64, device=dev)
+        _lib.check(self._ctx.handle, _lib.load().stm_heldout(
+            self._ctx.handle, D, d_ptr.data_ptr(), d_ids.data_ptr(), d_cnt.data_ptr(), self._ptr("theta"),
+            self._ptr("beta_t"), out.data_ptr(), out.data_ptr() + 8 * D, self._stream()))
+        res = out.cpu().numpy()
+        return (float(res[D]), res[:D]) if return_doc_ll else float(res[D])
+
     def save_model(self, output_dir):
         os.makedirs(output_dir, exist_ok=True)
         np.save(os.path.join(output_dir, "beta_hat"), self.beta)

@@ -20,6 +20,7 @@ def main():
     ap.add_argument("--K", type=int, default=50)
     ap.add_argument("--V", type=int, default=10000)
     ap.add_argument("--tag", default=os.environ.get("STM_B200_LIB", "default"))
+    ap.add_argument("--heldout", action="store_true", help="also time STM.eval_heldout on the training corpus")
     a = ap.parse_args()
     import torch
     cache = f"/tmp/corpus_{a.docs}_{a.V}_{a.K}.npz"
@@ -64,6 +65,28 @@ def main():
         ka, kb = m._ctx.estep_kernel_ms()
         out.append(f"it{it}: estep {e0.elapsed_time(e1):7.2f} ms (A {ka:6.2f} + B {kb:5.2f})  nfev {d['nfev'].mean():5.1f}  nit {d['nit'].mean():4.2f} "
                    f"repair {np.mean(d['repair'] > 0):.2f}  mstep {tm*1e3:5.2f} ms  bound {b:.6f}")
+    if a.heldout:
+        m.eval_heldout((ptr, ids, cnt))   # warm-up (uploads the CSR again: timed below with the upload)
+        import ctypes as C
+        from strutopy_b200 import _lib as L_
+        d_ptr = torch.from_numpy(np.ascontiguousarray(ptr, np.int64)).cuda()
+        d_ids = torch.from_numpy(np.ascontiguousarray(ids, np.int32)).cuda()
+        d_cnt = torch.from_numpy(np.ascontiguousarray(cnt, np.float32)).cuda()
+        res = torch.empty(a.docs + 1, dtype=torch.float64, device="cuda")
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(10):
+            L_.check(m._ctx.handle, L_.load().stm_heldout(m._ctx.handle, a.docs, d_ptr.data_ptr(), d_ids.data_ptr(),
+                                                           d_cnt.data_ptr(), m._ptr("theta"), m._ptr("beta_t"),
+                                                           res.data_ptr(), res.data_ptr() + 8 * a.docs, m._stream()))
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / 10
+        nnz = int(ptr[-1])
+        gb = (nnz * (8 + 4 * a.K) + a.docs * (8 * a.K + 16)) / 1e9
+        out.append(f"heldout: {ms:.3f} ms per call over {a.docs} documents / {nnz} held-out words "
+                   f"({a.docs / ms * 1e3 / 1e6:.1f} M docs/s, {gb / ms * 1e3:.0f} GB/s algorithmic), mean ll {float(res[-1]):.6f}")
     print(f"== {a.tag}")
     print("\n".join(out), flush=True)
 
