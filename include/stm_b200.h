@@ -147,6 +147,27 @@ int stm_heldout_host(stm_ctx* ctx, int64_t D, const int64_t* doc_ptr, const int3
                      const float* count, const double* theta, const double* beta_kv, double* doc_ll,
                      double* mean);
 
+/* ---- spectral initialisation of beta ------------------------------------------
+ * Replaces spectral_init / gram / fastAnchor / recover_l2, /root/reference/src/modules/stm.py:30-296,
+ * over the context's resident corpus (stm_set_corpus).  Two phases, so that a document-sharded fit
+ * needs ONE all-reduce (of gram_dev) between them:
+ *   keep [n_keep]   HOST: the kept word ids in the reference's order, np.argsort(-wprob)[:maxV]
+ *                   (stm.py:57; left to the caller so that ties break exactly as NumPy breaks them)
+ *   gram_dev        DEVICE double [n_keep*n_keep + n_keep], caller-owned: this rank's part of
+ *                   Htilde'Htilde (row-major upper triangle; stm.py:145-149) followed by diag(Hhat)
+ *                   (stm.py:146).  stm_spectral_finish uses it as workspace (contents destroyed).
+ * stm_spectral_finish: Q = gram - Hhat and the row-sum assertion (stm.py:149-154; failing it returns
+ * STM_ERR_INVALID with the reference's message), fastAnchor (stm.py:160-226), recover_l2
+ * (stm.py:229-296; the per-word QP is solved exactly as NNLS), beta_new[:, keep] = beta, + 0.001/V,
+ * total-sum normalisation (stm.py:78-82).
+ *   wprob_keep [n_keep] HOST: wprob[keep] (stm.py:53-59)
+ *   beta_kv_dev     DEVICE double [K][V] out (reference layout)
+ *   anchor_out [K]  HOST out (may be NULL): anchors as indices into keep (fastAnchor's return value)
+ * Both block until done. */
+int stm_spectral_gram(stm_ctx* ctx, int n_keep, const int32_t* keep, double* gram_dev, void* stream);
+int stm_spectral_finish(stm_ctx* ctx, int n_keep, const int32_t* keep, const double* wprob_keep,
+                        double* gram_dev, double* beta_kv_dev, int32_t* anchor_out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -253,8 +253,16 @@ class STM:
 
     def init_beta(self):
         if self.init == "spectral":
-            from .spectral import spectral_init
-            b = spectral_init(pack_corpus(self.documents), self.K, self.V, maxV=5000)
+            # stm.py:420-423 -> spectral_init(documents, K, V, maxV=5000): Gram statistics of the local
+            # shard, one all-reduce, anchors + recovery replicated on every rank
+            from .spectral import spectral_on_context
+            totals = np.asarray(self.wcounts, dtype=np.float64)
+            if self._presharded_total is not None:
+                t = self._torch.from_numpy(totals.copy()).to(self._dev)
+                self._dist.all_reduce(t)
+                totals = t.cpu().numpy()
+            width = int(np.flatnonzero(totals).max()) + 1 if np.any(totals) else 1   # create_dtm's width, stm.py:119
+            b = spectral_on_context(self._ctx, self._torch, self._dev, totals[:width], maxV=5000, dist=self._dist)
         elif self.init == "random":
             # stm.py:425-429: gamma(0.1, 1) from the legacy RNG seeded in the constructor, row-normalised
             b = np.random.gamma(0.1, 1, self.V * self.K).reshape(self.K, self.V)

@@ -14,6 +14,9 @@ Fixtures (all inputs are stored next to the reference's outputs so tests need no
   em_c1.npz            config 1 (D=200 V=500 K=5, 1 covariate) full EM to convergence: ELBO trace + final state
   em_toy_ctm.npz       the reference's own tests/test_integration.py toy pipeline (K=3, CTM, 2 iterations)
   wiki_corpus.npz      the reference's shipped wiki BoW corpus + X + its shipped iteration-0 ELBOs (K=50, 70)
+  spectral.npz         spectral_init (stm.py:30-84) of the live reference, `solve_qp` shimmed by exact NNLS
+                       (tools/ref_shims.py): two synthetic corpora (vocabulary truncated by maxV / not
+                       truncated) and the shipped wiki corpus at K=20 (anchors + every 8th kept column)
 
 beta in the state-injected fixtures is rounded to fp32-representable values BEFORE the reference
 runs, so the fp32-beta CUDA path sees bit-identical inputs.
@@ -239,6 +242,49 @@ def wiki_corpus():
     save("wiki_corpus.npz", out)
 
 
+def spectral():
+    """spectral_init of the live reference.  Case t: V=900 > maxV=500 (the `keep` cut is exercised);
+    case f: every word kept; case w: the shipped wiki corpus, K=20, maxV=5000 as STM.init_beta calls it."""
+    sys.path.insert(0, os.path.join(HERE, ".."))
+    from conftest import synthetic_corpus
+    out = {}
+    for tag, (D, V, K, maxV, n_words, seed) in dict(t=(400, 900, 8, 500, 60, 7), f=(1500, 120, 6, 5000, 80, 11)).items():
+        ptr, ids, cnt, _, _ = synthetic_corpus(D, V, K, n_words=n_words, seed=seed)
+        if maxV >= V:  # no truncation: every word must occur (stm.py:152-154 asserts on empty rows) -> compact ids
+            seen = np.unique(ids)
+            ids = np.searchsorted(seen, ids).astype(np.int32)
+            V = len(seen)
+        docs = [[(int(ids[j]), int(cnt[j])) for j in range(ptr[d], ptr[d + 1])] for d in range(D)]
+        dtm = stm_mod.create_dtm(docs)
+        wprob = np.array(np.sum(dtm, axis=0) / np.sum(dtm)).flatten()
+        keep = np.argsort(-1 * wprob)[:maxV]
+        Q = stm_mod.gram(dtm[:, keep])
+        out[tag + "_Q"] = Q.toarray()
+        out[tag + "_anchor"] = np.intp(stm_mod.fastAnchor(Q, K, verbose=False))
+        out[tag + "_beta"] = stm_mod.spectral_init(docs, K, V, maxV=maxV, verbose=False)
+        out[tag + "_keep"] = keep
+        out[tag + "_cfg"] = np.array([D, V, K, maxV, n_words, seed])
+        out[tag + "_doc_ptr"], out[tag + "_word_id"], out[tag + "_count"] = ptr, ids, cnt.astype(np.int16)
+    import scipy.io
+    mm = scipy.io.mmread(os.path.join(REF_ART, "wiki_data", "BoW_corpus.mm")).tocsr()
+    mm.sort_indices()
+    docs = [[(int(mm.indices[j]), int(mm.data[j])) for j in range(mm.indptr[d], mm.indptr[d + 1])]
+            for d in range(mm.shape[0])]
+    K, V = 20, mm.shape[1]
+    dtm = stm_mod.create_dtm(docs)
+    wprob = np.array(np.sum(dtm, axis=0) / np.sum(dtm)).flatten()
+    keep = np.argsort(-1 * wprob)[:5000]
+    out["w_anchor"] = np.intp(stm_mod.fastAnchor(stm_mod.gram(dtm[:, keep]), K, verbose=False))
+    beta = stm_mod.spectral_init(docs, K, V, maxV=5000, verbose=False)
+    out["w_keep"] = keep
+    out["w_cols"] = keep[::8]
+    out["w_beta_cols"] = beta[:, keep[::8]]
+    out["w_beta_rowsum"] = beta.sum(axis=1)
+    out["w_beta_dropped"] = np.float64(beta[0, np.setdiff1d(np.arange(V), keep)[0]])
+    out["w_cfg"] = np.array([mm.shape[0], V, K, 5000])
+    save("spectral.npz", out)
+
+
 ALL = dict(
     kat_small=kat_small,
     estep_K5=lambda: estep_fixture("estep_K5.npz", 5, 500, 200, 12345, {0, 2}, 3),
@@ -248,6 +294,7 @@ ALL = dict(
     em_c1=em_c1,
     em_toy_ctm=em_toy_ctm,
     wiki_corpus=wiki_corpus,
+    spectral=spectral,
 )
 
 if __name__ == "__main__":

@@ -26,19 +26,19 @@ class _Dictionary(dict):
 
 
 def _nnls_solve_qp(P, q, G=None, h=None, A=None, b=None, lb=None, ub=None, solver=None, **kw):
-    """min 0.5 x'Px + q'x s.t. Gx<=h, Ax=b — only what recover_l2 (stm.py:245-285) asks for."""
-    from scipy.optimize import minimize
+    """min 0.5 x'Px + q'x s.t. x <= 0 — exactly what recover_l2 (stm.py:245-285) asks quadprog for
+    (G = I, h = 0, no equality constraint).  With w = -x and P = R'R (Cholesky) this is the NNLS
+    problem min ||R w - R^-T q||, w >= 0: strictly convex, so the minimiser is unique and equals
+    quadprog's up to solver rounding."""
+    from scipy.linalg import cholesky, solve_triangular
+    from scipy.optimize import nnls
 
     n = P.shape[0]
-    cons = []
-    if G is not None:
-        cons.append({"type": "ineq", "fun": lambda x: h - G @ x, "jac": lambda x: -G})
-    if A is not None:
-        cons.append({"type": "eq", "fun": lambda x: A @ x - b, "jac": lambda x: A})
-    x0 = np.full(n, 1.0 / n)
-    res = minimize(lambda x: 0.5 * x @ P @ x + q @ x, x0, jac=lambda x: P @ x + q,
-                   constraints=cons, method="SLSQP", options={"maxiter": 500, "ftol": 1e-14})
-    return res.x
+    assert A is None and b is None and lb is None and ub is None
+    assert np.array_equal(G, np.eye(n)) and not np.any(h)
+    R = cholesky(P, lower=False)
+    w, _ = nnls(R, solve_triangular(R, q, trans="T", lower=False), maxiter=30 * n)
+    return -w
 
 
 def install():
