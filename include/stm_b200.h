@@ -36,7 +36,12 @@ enum {
 };
 
 /* model type / regression mode of update_mu (stm.py:636-711) */
-enum { STM_MODEL_STM = 0, STM_MODEL_CTM = 1 };
+enum {
+    STM_MODEL_STM = 0,        /* mode="ols":   LinearRegression (stm.py:690-694) */
+    STM_MODEL_CTM = 1,        /* column mean of eta (stm.py:648-651) */
+    STM_MODEL_STM_RIDGE = 2,  /* mode="ridge": sklearn Ridge(alpha=0.1) (stm.py:684-688) */
+    STM_MODEL_STM_LASSO = 3   /* mode="lasso": sklearn Lasso(alpha=1)   (stm.py:678-682) */
+};
 
 /* ---- lifecycle --------------------------------------------------------------------------------- */
 
@@ -105,7 +110,9 @@ int stm_moments(stm_ctx* ctx, const double* eta_dev, const double* x_dev, int p,
 /* M_step (stm.py:622-634) from the (all-reduced) statistics:
  *   update_mu   (stm.py:636-711): centred min-norm OLS (sklearn LinearRegression semantics,
  *               cond=1e-6), intercept dropped: gamma_t_dev [p][K1], mu_dev[D][K1] = X gamma'
- *               (CTM: mu = column mean of eta)
+ *               (CTM: mu = column mean of eta; STM_MODEL_STM_RIDGE / _LASSO: the reference's
+ *               regularised modes — centred Ridge(0.1) system, or sklearn's coordinate descent
+ *               with its duality-gap stop, both evaluated on the reduced moments)
  *   update_sigma(stm.py:713-728): sigma_dev [K1][K1], shrunk by sigprior
  *   update_beta (stm.py:739-745): beta_t_dev float [A][V][TS] (A>1: the reference normalises over
  *               the topic axis, kept), optionally beta64_t_dev double [A][V][TS] (may be NULL)

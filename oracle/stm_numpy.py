@@ -249,3 +249,61 @@ def eval_heldout(doc_ptr, word_id, count, theta, beta, return_doc_ll=False):
             doc_ll[i] = np.sum(word_ll) / np.sum(c)
     mean = np.mean(doc_ll)
     return (mean, doc_ll) if return_doc_ll else mean
+
+
+def lasso_from_moments(G, B, yy, N, alpha=1.0, tol=1e-4, max_iter=1000):
+    """sklearn Lasso(alpha).fit on centred data, restated on the moments G = Xc'Xc (p x p), B = Xc'Yc
+    (p x T), yy[t] = yc_t'yc_t — the form the device M-step evaluates after the all-reduce
+    (stm_b200.cu lasso_gamma_kernel).  Follows sklearn/linear_model/_cd_fast.pyx
+    enet_coordinate_descent (1.9.0): cyclic coordinate descent, gap-safe screening, duality-gap stop at
+    tol * y'y, with X_j'R = b_j - (Gw)_j, R'R = yy - 2 w'b + w'Gw, R'y = yy - w'b.  -> coef (T x p)."""
+    p, T = B.shape
+    a = alpha * N
+    coef = np.zeros((T, p))
+    for t in range(T):
+        b, w = B[:, t], np.zeros(p)
+        excl = np.zeros(p, bool)
+        tl = tol * yy[t]
+
+        def gap_enet():
+            gw = G @ w
+            xta = b - gw
+            dn = np.abs(xta).max()
+            r2, ry = yy[t] - 2 * w @ b + w @ gw, yy[t] - w @ b
+            scale = a / dn if dn > a else 1.0
+            return 0.5 * r2 + a * np.abs(w).sum() - (-0.5 * scale ** 2 * r2 + scale * ry), dn, xta
+
+        def screen(first, gap, dn, xta):
+            for j in range(p):
+                if first:
+                    if G[j, j] == 0:
+                        w[j], excl[j] = 0.0, True
+                        continue
+                elif excl[j]:
+                    continue
+                dj = (1 - abs(xta[j] / max(a, dn))) / np.sqrt(G[j, j])
+                if dj <= np.sqrt(2 * gap) / a:
+                    excl[j] = False
+                else:
+                    w[j], excl[j] = 0.0, True
+
+        gap, dn, xta = gap_enet()
+        if not gap <= tl:
+            screen(True, gap, dn, xta)
+            for it in range(max_iter):
+                w_max = d_w_max = 0.0
+                for j in range(p):
+                    if excl[j] or G[j, j] == 0:
+                        continue
+                    wj = w[j]
+                    tmp = (b[j] - G[j] @ w) + wj * G[j, j]
+                    w[j] = np.sign(tmp) * max(abs(tmp) - a, 0.0) / G[j, j]
+                    d_w_max = max(d_w_max, abs(w[j] - wj))
+                    w_max = max(w_max, abs(w[j]))
+                if w_max == 0.0 or d_w_max / w_max <= tol or it == max_iter - 1:
+                    gap, dn, xta = gap_enet()
+                    if gap <= tl:
+                        break
+                    screen(False, gap, dn, xta)
+        coef[t] = w
+    return coef

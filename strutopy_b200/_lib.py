@@ -11,7 +11,7 @@ LIB_PATH = os.environ.get("STM_B200_LIB") or os.path.join(_HERE, "libstm_b200.so
 
 STM_OK = 0
 STM_ERR_INVALID, STM_ERR_CUDA, STM_ERR_NOT_PD, STM_ERR_UNSUPPORTED, STM_ERR_NO_CORPUS = -1, -2, -3, -4, -5
-MODEL_STM, MODEL_CTM = 0, 1
+MODEL_STM, MODEL_CTM, MODEL_STM_RIDGE, MODEL_STM_LASSO = 0, 1, 2, 3
 
 EXPORTS = [
     "stm_create", "stm_destroy", "stm_last_error", "stm_beta_stride", "stm_launch_count", "stm_estep_kernel_ms",

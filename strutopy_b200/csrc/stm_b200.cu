@@ -320,9 +320,11 @@ __global__ void center_moments_kernel(const double* __restrict__ stats, const lo
 }
 // gamma_t [p][K1] = pinv(G) R with scipy.linalg.lstsq(cond=1e-6) semantics on the centred design:
 // singular values of Xc are sqrt(lam); those <= 1e-6 * max are dropped (min-norm solution).
+// ridge > 0: sklearn Ridge(alpha=ridge) on the centred design, (Xc'Xc + ridge I) gamma = Xc'eta_c
+// (stm.py:684-688; _ridge.py's dense 'cholesky' solver solves exactly this system).
 __global__ void solve_gamma_kernel(const double* __restrict__ Vec /*col-major p x p*/, const double* __restrict__ lam,
-                                   const double* __restrict__ R, int p, int K1, double* __restrict__ tmp /*p*K1*/,
-                                   double* __restrict__ gamma_t) {
+                                   const double* __restrict__ R, int p, int K1, double ridge,
+                                   double* __restrict__ tmp /*p*K1*/, double* __restrict__ gamma_t) {
     double lmax = 0.0;
     for (int i = 0; i < p; ++i) lmax = fmax(lmax, lam[i]);
     const double cut = 1e-12 * lmax;  // (1e-6)^2 on eigenvalues of Xc'Xc
@@ -331,7 +333,8 @@ __global__ void solve_gamma_kernel(const double* __restrict__ Vec /*col-major p 
         const int e = idx / K1, k = idx % K1;
         double s = 0.0;
         for (int i = 0; i < p; ++i) s += Vec[(size_t)e * p + i] * R[(size_t)i * K1 + k];
-        tmp[idx] = (lam[e] > cut && lam[e] > 0.0) ? s / lam[e] : 0.0;
+        if (ridge > 0.0) tmp[idx] = s / (fmax(lam[e], 0.0) + ridge);
+        else tmp[idx] = (lam[e] > cut && lam[e] > 0.0) ? s / lam[e] : 0.0;
     }
     __syncthreads();
     for (int idx = threadIdx.x; idx < p * K1; idx += blockDim.x) {
@@ -340,6 +343,84 @@ __global__ void solve_gamma_kernel(const double* __restrict__ Vec /*col-major p 
         for (int e = 0; e < p; ++e) s += Vec[(size_t)e * p + i] * tmp[(size_t)e * K1 + k];
         gamma_t[idx] = s;
     }
+}
+// sklearn Lasso(alpha=1, fit_intercept=True).fit(X, eta).coef_ (stm.py:678-682) on the reduced moments.
+// sklearn fits each target separately by cyclic coordinate descent (linear_model/_cd_fast.pyx,
+// enet_coordinate_descent, installed 1.9.0: gap-safe screening, duality-gap stop at tol * y'y,
+// tol = 1e-4, max_iter = 1000) on the centred data with l1_reg = alpha * n_samples.  Every quantity it
+// forms is a function of G = Xc'Xc, b = Xc'y_c and yy = y_c'y_c:
+//   X_j'R = b_j - (G w)_j,   R'R = yy - 2 w'b + w'G w,   R'y = yy - w'b
+// so the same iteration runs here from the all-reduced moments, one thread per topic.
+// ws: 3 p doubles per topic (w | XtA | flags).
+__global__ void lasso_gamma_kernel(const double* __restrict__ G, const double* __restrict__ B /*p x K1*/,
+                                   const double* __restrict__ stats, const long long* __restrict__ off, int p, int K1,
+                                   double alpha_per_sample, double* __restrict__ ws, double* __restrict__ gamma_t) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= K1) return;
+    const double N = stats[off[3]];
+    const double se = stats[off[4] + k];
+    const double yy = stats[off[8] + (size_t)k * K1 + k] - (se / N) * se;
+    const double alpha = alpha_per_sample * N;
+    double* w = ws + (size_t)k * 3 * p;
+    double* XtA = w + p;
+    double* excl = XtA + p;          // 0 active, 1 excluded
+    for (int j = 0; j < p; ++j) { w[j] = 0.0; excl[j] = 0.0; }
+    const double tol = 1e-4 * yy;
+    double gap = 0.0, dual_norm = 0.0;
+    auto bj = [&](int j) { return B[(size_t)j * K1 + k]; };
+    auto gw = [&](int j) { double s = 0.0; for (int i = 0; i < p; ++i) s += G[(size_t)j * p + i] * w[i]; return s; };
+    auto gap_enet = [&]() {
+        double wb = 0.0, wgw = 0.0, l1 = 0.0;
+        dual_norm = 0.0;
+        for (int j = 0; j < p; ++j) {
+            const double g = gw(j);
+            XtA[j] = bj(j) - g;
+            dual_norm = fmax(dual_norm, fabs(XtA[j]));
+            wb += w[j] * bj(j);
+            wgw += w[j] * g;
+            l1 += fabs(w[j]);
+        }
+        const double R2 = yy - 2.0 * wb + wgw, Ry = yy - wb;
+        const double primal = 0.5 * R2 + alpha * l1;
+        const double scale = (dual_norm > alpha) ? alpha / dual_norm : 1.0;
+        const double dual = -0.5 * (scale * scale) * R2 + scale * Ry;
+        gap = primal - dual;
+    };
+    auto screen = [&](bool first) {
+        for (int j = 0; j < p; ++j) {
+            if (first) {
+                if (G[(size_t)j * p + j] == 0.0) { w[j] = 0.0; excl[j] = 1.0; continue; }
+            } else if (excl[j] != 0.0) continue;
+            const double xt = XtA[j] / fmax(alpha, dual_norm);
+            const double dj = (1.0 - fabs(xt)) / sqrt(G[(size_t)j * p + j]);
+            if (dj <= sqrt(2.0 * gap) / alpha) excl[j] = 0.0;
+            else { w[j] = 0.0; excl[j] = 1.0; }
+        }
+    };
+    gap_enet();
+    if (!(gap <= tol)) {
+        screen(true);
+        for (int it = 0; it < 1000; ++it) {
+            double w_max = 0.0, d_w_max = 0.0;
+            for (int j = 0; j < p; ++j) {
+                if (excl[j] != 0.0) continue;
+                const double gjj = G[(size_t)j * p + j];
+                if (gjj == 0.0) continue;
+                const double wj = w[j];
+                const double tmp = (bj(j) - gw(j)) + wj * gjj;
+                const double sgn = (tmp > 0.0) ? 1.0 : ((tmp < 0.0) ? -1.0 : 0.0);
+                w[j] = sgn * fmax(fabs(tmp) - alpha, 0.0) / gjj;
+                d_w_max = fmax(d_w_max, fabs(w[j] - wj));
+                w_max = fmax(w_max, fabs(w[j]));
+            }
+            if (w_max == 0.0 || d_w_max / w_max <= 1e-4 || it == 999) {
+                gap_enet();
+                if (gap <= tol) break;
+                screen(false);
+            }
+        }
+    }
+    for (int j = 0; j < p; ++j) gamma_t[(size_t)j * K1 + k] = w[j];
 }
 // sigma = ((eta-mu)'(eta-mu) + sigma_ss)/N with the residual Gram expanded from the global moments,
 // then the sigprior shrinkage (stm.py:723-728).  mode: 0 STM (mu = X gamma'), 1 CTM (mu = mean eta).
@@ -840,6 +921,8 @@ int stm_mstep(stm_ctx* ctx, const double* stats_dev, const double* x_dev, int p,
     if (!ctx || !stats_dev || !mu_dev || !sigma_dev || !beta_t_dev) return STM_ERR_INVALID;
     if (!(sigprior >= 0.0 && sigprior <= 1.0))
         return fail(ctx, STM_ERR_INVALID, "weight needs to be defined between 0 and 1");  // stm.py:721
+    const int reg_mode = model;   // STM_MODEL_STM (ols) / STM_MODEL_STM_RIDGE / STM_MODEL_STM_LASSO / STM_MODEL_CTM
+    if (model == STM_MODEL_STM_RIDGE || model == STM_MODEL_STM_LASSO) model = STM_MODEL_STM;
     if (model != STM_MODEL_STM && model != STM_MODEL_CTM)
         return fail(ctx, STM_ERR_INVALID, "Updating the topical prevalence parameter requires a mode");  // stm.py:709
     if (model == STM_MODEL_STM && (p < 1 || !x_dev || !gamma_t_dev))
@@ -853,7 +936,7 @@ int stm_mstep(stm_ctx* ctx, const double* stats_dev, const double* x_dev, int p,
     int64_t off[10];
     layout(ctx, model == STM_MODEL_STM ? p : p, off);
     // small workspace carve-up
-    const int64_t need = 16 + (int64_t)p * p + p + 3LL * p * K1 + 2LL * TS * ctx->A;
+    const int64_t need = 16 + 2LL * p * p + p + 5LL * p * K1 + 2LL * TS * ctx->A;
     if (need > ctx->msmall_len) {
         cudaFree(ctx->d_msmall);
         ctx->msmall_len = need + 1024;
@@ -865,6 +948,7 @@ int stm_mstep(stm_ctx* ctx, const double* stats_dev, const double* x_dev, int p,
     double* R = lam + p;
     double* tmp = R + (int64_t)p * K1;
     double* rowsum = tmp + (int64_t)p * K1;
+    double* lasso_ws = rowsum + 2LL * TS * ctx->A;     // lasso: 3 p K1
     long long hoff[10];
     for (int i = 0; i < 10; ++i) hoff[i] = off[i];
     CU(cudaMemcpyAsync(d_off, hoff, sizeof(hoff), cudaMemcpyHostToDevice, st));
@@ -872,6 +956,10 @@ int stm_mstep(stm_ctx* ctx, const double* stats_dev, const double* x_dev, int p,
     // ---- update_mu ---------------------------------------------------------------------------
     if (model == STM_MODEL_STM) {
         center_moments_kernel<<<1, 256, 0, st>>>(stats_dev, d_off, p, K1, G, R);
+        if (reg_mode == STM_MODEL_STM_LASSO) {
+            lasso_gamma_kernel<<<(K1 + 63) / 64, 64, 0, st>>>(G, R, stats_dev, d_off, p, K1, 1.0, lasso_ws, gamma_t_dev);
+            ctx->launches += 2;
+        } else {
         if (ctx->syevd_p != p) {
             int lwork = 0;
             CS(cusolverDnDsyevd_bufferSize(ctx->cusolver, CUSOLVER_EIG_MODE_VECTOR, CUBLAS_FILL_MODE_LOWER, p, G, p,
@@ -883,8 +971,10 @@ int stm_mstep(stm_ctx* ctx, const double* stats_dev, const double* x_dev, int p,
         }
         CS(cusolverDnDsyevd(ctx->cusolver, CUSOLVER_EIG_MODE_VECTOR, CUBLAS_FILL_MODE_LOWER, p, G, p, lam,
                             ctx->d_syevd_work, ctx->syevd_lwork, ctx->d_info + 1));
-        solve_gamma_kernel<<<1, 256, 0, st>>>(G, lam, R, p, K1, tmp, gamma_t_dev);
+        solve_gamma_kernel<<<1, 256, 0, st>>>(G, lam, R, p, K1, reg_mode == STM_MODEL_STM_RIDGE ? 0.1 : 0.0, tmp,
+                                              gamma_t_dev);
         ctx->launches += 2;
+        }
         // mu (column-major K1 x D) = gamma_t (column-major K1 x p) * X (column-major p x D)
         if (D > 0) {
             const double one = 1.0, zero = 0.0;
@@ -945,13 +1035,16 @@ int stm_estep_host(stm_ctx* ctx, const double* beta, const double* mu, const dou
     CU(cudaSetDevice(ctx->device));
     const int K = ctx->K, K1 = ctx->K1, V = ctx->V, A = ctx->A, TS = ctx->TS;
     const int64_t D = ctx->D;
-    // the reference's siginv is diagonal by construction (stm.py:501); anything else is not this path
+    // the reference's siginv is diagonal by construction (stm.py:501: element-wise product of a lower- and
+    // an upper-triangular inverse); anything else is not this path.  When LAPACK's LU pivots inside
+    // np.linalg.inv(chol) the "zero" triangle holds rounding noise (~1e-17), so off-diagonals are accepted
+    // up to 1e-9 of the geometric mean of their diagonal entries (their effect is below fp64 resolution).
     std::vector<double> prior(K1 + 1);
     for (int i = 0; i < K1; ++i)
         for (int j = 0; j < K1; ++j) {
             const double s = siginv[(size_t)i * K1 + j];
             if (i == j) prior[i] = s;
-            else if (s != 0.0)
+            else if (!(std::fabs(s) <= 1e-9 * std::sqrt(std::fabs(siginv[(size_t)i * K1 + i] * siginv[(size_t)j * K1 + j]))))
                 return fail(ctx, STM_ERR_UNSUPPORTED, "siginv must be diagonal (as produced by stm.py:501)");
         }
     prior[K1] = sigmaentropy;

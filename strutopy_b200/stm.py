@@ -319,20 +319,18 @@ class STM:
 
     def _mstep_device(self):
         L, h, st = _lib.load(), self._ctx.handle, self._stream()
-        model = _lib.MODEL_STM if self.model == "STM" else _lib.MODEL_CTM
-        if self.model == "STM" and self.mode in ("lasso", "ridge"):
-            self._host_regularised_mu()
-            model = -1
-        _lib.check(h, L.stm_mstep(h, self._ptr("stats"), self._ptr("x"), self._p,
-                                  _lib.MODEL_STM if model == -1 else model, float(self.sigma_prior),
+        if self.model != "STM":
+            model = _lib.MODEL_CTM
+        else:   # stm.py:673-694: any other mode string falls back to 'ols' (after a printed notice)
+            if self.mode not in ["lasso", "ridge", "ols"]:
+                print("Need to specify the estimation mode of prevalence covariate coefficients. Uses default 'ols'.")
+            model = {"ridge": _lib.MODEL_STM_RIDGE, "lasso": _lib.MODEL_STM_LASSO}.get(self.mode, _lib.MODEL_STM)
+        _lib.check(h, L.stm_mstep(h, self._ptr("stats"), self._ptr("x"), self._p, model, float(self.sigma_prior),
                                   self._ptr("gamma_t"), self._ptr("mu"), self._ptr("sigma"),
                                   self._ptr("beta_t"), None, st))
         if self.model == "STM":
             self.gamma = self._d["gamma_t"][:self._p].t().contiguous().cpu().numpy()  # K1 x p, stm.py:703
         self._invalidate("mu", "sigma", "beta")
-
-    def _host_regularised_mu(self):
-        raise NotImplementedError("mode='lasso'/'ridge' (stm.py:678-688) is not on the accelerated path yet; use 'ols'")
 
     def E_step(self):
         """stm.py:489-597 — returns (beta_ss, sigma_ss) as host arrays in the reference's layout."""

@@ -14,6 +14,10 @@ Fixtures (all inputs are stored next to the reference's outputs so tests need no
   em_c1.npz            config 1 (D=200 V=500 K=5, 1 covariate) full EM to convergence: ELBO trace + final state
   em_toy_ctm.npz       the reference's own tests/test_integration.py toy pipeline (K=3, CTM, 2 iterations)
   wiki_corpus.npz      the reference's shipped wiki BoW corpus + X + its shipped iteration-0 ELBOs (K=50, 70)
+  mstep_modes.npz      update_mu / update_sigma of the live reference in its regularised modes (stm.py:678-688:
+                       sklearn Lasso(alpha=1), Ridge(alpha=0.1)) and 'ols', on injected eta with strong
+                       covariate effects (so that the Lasso coefficients are not all zero); binary and
+                       one-hot-encoded (3-level) designs
   spectral.npz         spectral_init (stm.py:30-84) of the live reference, `solve_qp` shimmed by exact NNLS
                        (tools/ref_shims.py): two synthetic corpora (vocabulary truncated by maxV / not
                        truncated) and the shipped wiki corpus at K=20 (anchors + every 8th kept column)
@@ -242,6 +246,43 @@ def wiki_corpus():
     save("wiki_corpus.npz", out)
 
 
+def mstep_modes():
+    """M1 in every `mode` (stm.py:673-706) on injected eta.  eta = X Gamma' + noise with |Gamma| up to 9:
+    the Lasso threshold alpha * N is crossed for some (topic, covariate) pairs and not for others."""
+    sys.path.insert(0, os.path.join(HERE, ".."))
+    from conftest import synthetic_corpus
+    out = {}
+    D, V, K = 240, 300, 7
+    ptr, ids, cnt, _, _ = synthetic_corpus(D, V, K, n_words=40, seed=21)
+    docs = [[(int(ids[j]), int(cnt[j])) for j in range(ptr[d], ptr[d + 1])] for d in range(D)]
+    out["doc_ptr"], out["word_id"], out["count"] = ptr, ids, cnt.astype(np.int16)
+    out["K"], out["V"] = np.int64(K), np.int64(V)
+    rng = np.random.default_rng(77)
+    designs = dict(bin=rng.integers(0, 2, size=(D, 2)).astype(np.float64),   # kept as is (exactly 0/1)
+                   cat=rng.integers(0, 3, size=(D, 1)).astype(np.float64))   # one-hot encoded -> 3 columns
+    sigma_ss = rng.normal(size=(K - 1, K - 1))
+    sigma_ss = sigma_ss @ sigma_ss.T * D
+    out["sigma_ss"] = sigma_ss
+    for dn, X in designs.items():
+        m = make_model(docs, {i: str(i) for i in range(V)}, K, X, 2)
+        cov = np.array(X)[:, None]
+        cov = np.squeeze(cov, axis=1)
+        if not np.array_equal(cov, cov.astype(bool)):
+            cov = np.concatenate([(cov[:, [j]] == np.unique(cov[:, j])[None, :]).astype(float) for j in range(cov.shape[1])], axis=1)
+        Gam = rng.choice([-9.0, -5.0, -0.7, 0.0, 0.4, 4.5, 8.0], size=(K - 1, cov.shape[1]))
+        eta = cov @ Gam.T + rng.normal(0, 0.8, size=(D, K - 1))
+        out[dn + "_X"], out[dn + "_eta"] = X, eta
+        for mode in ("ols", "ridge", "lasso"):
+            m.mode = mode
+            m.eta = eta.copy()
+            m.update_mu()
+            m.update_sigma(sigma_ss, 0.3)
+            out[f"{dn}_{mode}_gamma"], out[f"{dn}_{mode}_mu"], out[f"{dn}_{mode}_sigma"] = (
+                np.array(m.gamma), np.array(m.mu), np.array(m.sigma))
+            print(dn, mode, "nonzero gamma:", int(np.count_nonzero(m.gamma)), "of", m.gamma.size)
+    save("mstep_modes.npz", out)
+
+
 def spectral():
     """spectral_init of the live reference.  Case t: V=900 > maxV=500 (the `keep` cut is exercised);
     case f: every word kept; case w: the shipped wiki corpus, K=20, maxV=5000 as STM.init_beta calls it."""
@@ -295,6 +336,7 @@ ALL = dict(
     em_toy_ctm=em_toy_ctm,
     wiki_corpus=wiki_corpus,
     spectral=spectral,
+    mstep_modes=mstep_modes,
 )
 
 if __name__ == "__main__":

@@ -200,6 +200,26 @@ def test_mstep_vs_reference_fixture(name, pfx):
         np.testing.assert_allclose(m.beta, stm_numpy.update_beta(g[pfx + "beta_ss"]), rtol=2e-7, atol=1e-12)
 
 
+@pytest.mark.parametrize("design", ["bin", "cat"])
+@pytest.mark.parametrize("mode", ["ols", "ridge", "lasso"])
+def test_mstep_regularised_modes_vs_live_reference(design, mode):
+    """M1 in the reference's three regression modes (stm.py:673-706): sklearn LinearRegression /
+    Ridge(alpha=0.1) / Lasso(alpha=1), evaluated on the device from the reduced moments."""
+    from strutopy_b200 import STM
+    g = load_golden("mstep_modes.npz")
+    K, V = int(g["K"]), int(g["V"])
+    m = STM((g["doc_ptr"], g["word_id"], g["count"]), range(V), False, K, g[design + "_X"], False, 2, 0.3, 1e-5,
+            init_type="random", model_type="STM", mode=mode)
+    m.eta = g[design + "_eta"]
+    m.M_step(np.ones((K, V)), g["sigma_ss"])
+    ref = g[f"{design}_{mode}_gamma"]
+    if mode == "lasso":
+        np.testing.assert_array_equal(m.gamma == 0, ref == 0)
+    np.testing.assert_allclose(m.gamma, ref, rtol=1e-8, atol=1e-9)
+    np.testing.assert_allclose(m.mu, g[f"{design}_{mode}_mu"], rtol=1e-8, atol=1e-9)
+    np.testing.assert_allclose(m.sigma, g[f"{design}_{mode}_sigma"], rtol=1e-8, atol=1e-10)
+
+
 def test_front_estep_state_injection_matches_fixture():
     g = load_golden("estep_K20.npz")
     pfx = "it1_"

@@ -129,3 +129,25 @@ def test_em_toy_ctm_trace_c_oracle():
     np.testing.assert_allclose(r["bounds"], g["bounds"], rtol=1e-11)
     np.testing.assert_allclose(r["theta"], g["final_theta"], atol=1e-8)
     np.testing.assert_allclose(r["sigma"], g["final_sigma"], atol=1e-9)
+
+
+@pytest.mark.parametrize("design", ["bin", "cat"])
+def test_mstep_regularised_modes_vs_live_reference(design):
+    """update_mu in mode 'ols' / 'ridge' / 'lasso' (stm.py:673-706) + update_sigma with sigprior = 0.3: the
+    NumPy port against the live reference, and the moments form of sklearn's coordinate descent (what the
+    device M-step runs after the all-reduce) against the reference's Lasso coefficients."""
+    g = load_golden("mstep_modes.npz")
+    X, eta = g[design + "_X"], g[design + "_eta"]
+    for mode in ("ols", "ridge", "lasso"):
+        mu, gamma = stm_numpy.update_mu(eta, X, mode=mode)
+        np.testing.assert_allclose(gamma, g[f"{design}_{mode}_gamma"], rtol=1e-10, atol=1e-12)
+        np.testing.assert_allclose(mu, g[f"{design}_{mode}_mu"], rtol=1e-10, atol=1e-12)
+        np.testing.assert_allclose(stm_numpy.update_sigma(eta, mu, g["sigma_ss"], 0.3), g[f"{design}_{mode}_sigma"],
+                                   rtol=1e-10, atol=1e-12)
+    cov = stm_numpy.design_matrix(X)
+    xc, yc = cov - cov.mean(0), eta - eta.mean(0)
+    coef = stm_numpy.lasso_from_moments(xc.T @ xc, xc.T @ yc, (yc * yc).sum(0), len(eta))
+    ref = g[design + "_lasso_gamma"]
+    assert 0 < np.count_nonzero(ref) < ref.size          # the fixture exercises both sides of the threshold
+    np.testing.assert_array_equal(coef == 0, ref == 0)
+    np.testing.assert_allclose(coef, ref, rtol=1e-10, atol=1e-12)
