@@ -175,6 +175,20 @@ int stm_spectral_gram(stm_ctx* ctx, int n_keep, const int32_t* keep, double* gra
 int stm_spectral_finish(stm_ctx* ctx, int n_keep, const int32_t* keep, const double* wprob_keep,
                         double* gram_dev, double* beta_kv_dev, int32_t* anchor_out, void* stream);
 
+/* ---- synthetic corpus sampler ---------------------------------------------------
+ * Replaces CorpusCreation.sample_documents, /root/reference/src/modules/generate_docs.py:293-316:
+ * document d ~ Multinomial(n_words, theta_d beta), drawn on the device as n_words (topic, word) pairs per
+ * document so that theta @ beta (D x V, generate_docs.py:297) is never materialised.  Philox4x32-10
+ * keyed by `seed`: stateless and reproduced bit for bit by oracle/corpus_numpy.py.
+ *   theta_dev   double [D][K]  (rows need not be normalised: the inverse CDF is scaled by the row sum)
+ *   beta_kv_dev double [K][V]
+ *   doc_ptr_dev int64 [D+1], word_id_dev int32 [D*n_words], count_dev float [D*n_words]: CSR out,
+ *               ids ascending within a document; *nnz_out (HOST) = doc_ptr[D].  1 <= n_words <= 4096.
+ * K and V are the context's.  Blocks until done. */
+int stm_sample_corpus(stm_ctx* ctx, int64_t D, int n_words, const double* theta_dev,
+                      const double* beta_kv_dev, uint64_t seed, int64_t* doc_ptr_dev, int32_t* word_id_dev,
+                      float* count_dev, int64_t* nnz_out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

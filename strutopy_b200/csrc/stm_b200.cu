@@ -1177,3 +1177,4 @@ int stm_heldout_host(stm_ctx* ctx, int64_t D, const int64_t* doc_ptr, const int3
 }  // extern "C"
 
 #include "spectral.cuh"
+#include "corpus_gen.cuh"
