@@ -175,6 +175,23 @@ int stm_spectral_gram(stm_ctx* ctx, int n_keep, const int32_t* keep, double* gra
 int stm_spectral_finish(stm_ctx* ctx, int n_keep, const int32_t* keep, const double* wprob_keep,
                         double* gram_dev, double* beta_kv_dev, int32_t* anchor_out, void* stream);
 
+/* ---- content-covariate update of beta -------------------------------------------
+ * Replaces update_beta with lda_beta=False -> STM.mnreg, /root/reference/src/modules/stm.py:746-853:
+ * per word, sklearn PoissonRegressor(fit_intercept=False, alpha) of the (A K) counts beta_ss[a][k][v] on
+ * one-hot topic / aspect / interaction covariates (stm.py:769-793), kappa = coefficients (stm.py:841),
+ * beta = softmax over the vocabulary of (m + covar @ kappa), split by aspect (stm.py:847-853).
+ *   stats_dev    packed statistics (segment 0 = beta_ss, after the all-reduce)
+ *   logm_dev     double [V]: m = log(wcounts) - log(sum wcounts) (stm.py:795-797)
+ *   alpha        the L2 penalty (the reference uses 250, stm.py:758)
+ *   word_column  -1: word v is regressed on its own column v; >= 0: EVERY word is regressed on this
+ *                column — the reference as written uses 1 (`counts[:, [1]]`, stm.py:825)
+ *   beta_t_dev   float [A][V][TS] out; beta64_t_dev double [A][V][TS] out or NULL
+ *   kappa_dev    double [K+A+A*K+1][V] out or NULL (row K is the reference's empty column)
+ * The minimiser is unique (strictly convex); it is computed by damped Newton to ~1e-12, sklearn's lbfgs
+ * stops at a 1e-5 gradient: agreement ~1e-8.  A >= 2, A <= 8.  Blocks until done. */
+int stm_update_kappa(stm_ctx* ctx, const double* stats_dev, const double* logm_dev, double alpha,
+                     int word_column, float* beta_t_dev, double* beta64_t_dev, double* kappa_dev, void* stream);
+
 /* ---- synthetic corpus sampler ---------------------------------------------------
  * Replaces CorpusCreation.sample_documents, /root/reference/src/modules/generate_docs.py:293-316:
  * document d ~ Multinomial(n_words, theta_d beta), drawn on the device as n_words (topic, word) pairs per

@@ -17,7 +17,7 @@ EXPORTS = [
     "stm_create", "stm_destroy", "stm_last_error", "stm_beta_stride", "stm_launch_count", "stm_estep_kernel_ms",
     "stm_set_corpus", "stm_stats_layout", "stm_prologue", "stm_estep", "stm_moments", "stm_mstep",
     "stm_beta_to_wordmajor", "stm_wordmajor_to_kv", "stm_estep_host", "stm_heldout", "stm_heldout_host",
-    "stm_spectral_gram", "stm_spectral_finish", "stm_sample_corpus",
+    "stm_spectral_gram", "stm_spectral_finish", "stm_sample_corpus", "stm_update_kappa",
 ]
 
 _lib = None
@@ -54,6 +54,7 @@ def load():
     L.stm_spectral_gram.argtypes = [vp, i32, vp, vp, vp]
     L.stm_spectral_finish.argtypes = [vp, i32, vp, vp, vp, vp, vp, vp]
     L.stm_sample_corpus.argtypes = [vp, i64, i32, vp, vp, C.c_uint64, vp, vp, vp, C.POINTER(i64), vp]
+    L.stm_update_kappa.argtypes = [vp, vp, vp, dbl, i32, vp, vp, vp, vp]
     L.stm_set_corpus.argtypes = [vp, i64, vp, vp, vp, vp]
     L.stm_stats_layout.argtypes = [vp, i32, C.POINTER(i64)]
     L.stm_prologue.argtypes = [vp, vp, vp, vp, vp]

@@ -1178,3 +1178,4 @@ int stm_heldout_host(stm_ctx* ctx, int64_t D, const int64_t* doc_ptr, const int3
 
 #include "spectral.cuh"
 #include "corpus_gen.cuh"
+#include "mnreg.cuh"

@@ -8,7 +8,9 @@ on assignment, so reference-style state injection (`model.beta = ...`) keeps wor
 
 New keyword arguments (all optional, defaults reproduce the reference): `device`; `distributed`
 (shard the documents over the ranks of the initialised torch.distributed group); `presharded`
-(with `distributed`: `documents`, `X`, `beta_index` already are this rank's shard).
+(with `distributed`: `documents`, `X`, `beta_index` already are this rank's shard); `mnreg_column`
+(content model, `lda_beta=False`: None regresses word v on its own count column; 1 reproduces the reference
+AS WRITTEN, whose `mnreg` regresses every word on column 1, stm.py:825 — DESIGN.md §10.4).
 """
 import logging
 import os
@@ -56,7 +58,7 @@ class STM:
     def __init__(self, documents, dictionary, content, K, X, kappa_interactions, max_em_iter,
                  sigma_prior, convergence_threshold, lda_beta=True, beta_index=None, A=None,
                  dtype=np.float32, init_type="spectral", model_type="STM", mode="ols",
-                 device=None, distributed=False, presharded=False):
+                 device=None, distributed=False, presharded=False, mnreg_column=None):
         """Keyword-compatible with stm.py:311-329.  `documents`: list of [(word_id, count), ...] (or a
         pre-packed CSR triple); `dictionary`: anything with len() and item lookup."""
         np.random.seed(123456)  # stm.py:361 (`random` there is numpy.random)
@@ -87,10 +89,12 @@ class STM:
             raise ValueError("Number of topics must be specified")  # stm.py:393-394
         if self.A == 1:
             logging.warning("no dimension for the topical content provided")
-        if not self.LDAbeta:
+        self.mnreg_column = mnreg_column
+        self.kappa = None
+        if not self.LDAbeta and not (self.interactions and self.A and int(self.A) >= 2):
             raise NotImplementedError(
-                "lda_beta=False (content-covariate kappa update, stm.py:749-853) is outside the "
-                "accelerated path: the reference implementation of mnreg does not run (SURVEY.md §2)")
+                "lda_beta=False (STM.mnreg, stm.py:749-853) is the CONTENT model: it needs kappa_interactions=True, "
+                "A >= 2 and beta_index (the reference's own A == 1 branch indexes beta_ss[1] of a K x V array)")
         if self.model not in ("STM", "CTM"):
             raise ValueError('Updating the topical prevalence parameter requires a mode. Choose from '
                              '"CTM", "Pooled" or "L1" (default).')  # stm.py:708-711
@@ -330,7 +334,29 @@ class STM:
                                   self._ptr("beta_t"), None, st))
         if self.model == "STM":
             self.gamma = self._d["gamma_t"][:self._p].t().contiguous().cpu().numpy()  # K1 x p, stm.py:703
+        if not self.LDAbeta:
+            self._update_kappa_device()
         self._invalidate("mu", "sigma", "beta")
+
+    def _update_kappa_device(self):
+        """update_beta with lda_beta=False -> mnreg (stm.py:746-853): kappa and beta from the reduced beta_ss."""
+        torch = self._torch
+        L, h, st = _lib.load(), self._ctx.handle, self._stream()
+        if "logm" not in self._d:
+            w = np.asarray(self.wcounts, dtype=np.float64)
+            if self._presharded_total is not None:
+                t = torch.from_numpy(w.copy()).to(self._dev)
+                self._dist.all_reduce(t)
+                w = t.cpu().numpy()
+            with np.errstate(divide="ignore"):
+                m = np.log(w) - np.log(np.sum(w))                      # stm.py:795-797
+            self._d["logm"] = torch.from_numpy(m).to(self._dev)
+            p_rows = self.K + self._nA + self._nA * self.K + 1
+            self._d["kappa"] = torch.zeros((p_rows, self.V), dtype=torch.float64, device=self._dev)
+        col = -1 if self.mnreg_column is None else int(self.mnreg_column)
+        _lib.check(h, L.stm_update_kappa(h, self._ptr("stats"), self._ptr("logm"), 250.0, col, self._ptr("beta_t"),
+                                         None, self._ptr("kappa"), st))
+        self.kappa = self._d["kappa"].cpu().numpy()
 
     def E_step(self):
         """stm.py:489-597 — returns (beta_ss, sigma_ss) as host arrays in the reference's layout."""

@@ -18,6 +18,8 @@ Fixtures (all inputs are stored next to the reference's outputs so tests need no
                        sklearn Lasso(alpha=1), Ridge(alpha=0.1)) and 'ols', on injected eta with strong
                        covariate effects (so that the Lasso coefficients are not all zero); binary and
                        one-hot-encoded (3-level) designs
+  mnreg.npz            STM.mnreg (stm.py:749-853) of the live reference (csr_matrix.A restored by the shim) on the
+                       content fixture's beta_ss: kappa and beta AS WRITTEN (every word regressed on column 1)
   spectral.npz         spectral_init (stm.py:30-84) of the live reference, `solve_qp` shimmed by exact NNLS
                        (tools/ref_shims.py): two synthetic corpora (vocabulary truncated by maxV / not
                        truncated) and the shipped wiki corpus at K=20 (anchors + every 8th kept column)
@@ -283,6 +285,22 @@ def mstep_modes():
     save("mstep_modes.npz", out)
 
 
+def mnreg():
+    g = dict(np.load(os.path.join(HERE, "estep_content.npz")))
+    K, V, A = int(g["K"]), int(g["V"]), int(g["A"])
+    D = len(g["doc_ptr"]) - 1
+    docs = [[(int(g["word_id"][j]), int(g["count"][j])) for j in range(g["doc_ptr"][d], g["doc_ptr"][d + 1])]
+            for d in range(D)]
+    m = make_model(docs, {i: str(i) for i in range(V)}, K, g["X"], 2, content=True, interactions=True, A=A,
+                   beta_index=g["aspect"])
+    m.LDAbeta = False
+    out = dict(K=np.int64(K), V=np.int64(V), A=np.int64(A), beta_ss=g["it0_beta_ss"], wcounts=np.array(m.wcounts))
+    m.update_beta(out["beta_ss"])                          # -> mnreg (stm.py:746-747)
+    out["kappa"] = np.array(m.kappa)
+    out["beta"] = np.stack(m.beta, axis=0)
+    save("mnreg.npz", out)
+
+
 def spectral():
     """spectral_init of the live reference.  Case t: V=900 > maxV=500 (the `keep` cut is exercised);
     case f: every word kept; case w: the shipped wiki corpus, K=20, maxV=5000 as STM.init_beta calls it."""
@@ -337,6 +355,7 @@ ALL = dict(
     wiki_corpus=wiki_corpus,
     spectral=spectral,
     mstep_modes=mstep_modes,
+    mnreg=mnreg,
 )
 
 if __name__ == "__main__":

@@ -42,6 +42,15 @@ np.testing.assert_allclose(md.sigma, ms.sigma, atol=1e-6)
 bss, sss = md.E_step(); md.M_step(bss, sss)
 bs2, ss2 = ms.E_step(); ms.M_step(bs2, ss2)
 np.testing.assert_allclose(bss, bs2, atol=1e-5); np.testing.assert_allclose(md.sigma, ms.sigma, atol=1e-6)
+# spectral initialisation over sharded documents: local Gram statistics, ONE all-reduce, replicated recovery
+sp = load_golden('spectral.npz')
+sdocs = (sp['f_doc_ptr'], sp['f_word_id'], sp['f_count'].astype(np.float64))
+Ks, Vs = int(sp['f_cfg'][2]), sp['f_beta'].shape[1]
+Xs = (np.arange(len(sdocs[0]) - 1) % 2).astype(np.float64)[:, None]
+bd = STM(sdocs, range(Vs), False, Ks, Xs, False, 2, 0, 0.0, init_type='spectral', device=rank, distributed=True).beta
+b1 = STM(sdocs, range(Vs), False, Ks, Xs, False, 2, 0, 0.0, init_type='spectral', device=rank, distributed=False).beta
+assert np.abs(bd - b1).max() <= 2e-7 * b1.max(), np.abs(bd - b1).max()   # beta is stored in fp32
+assert np.abs(bd - sp['f_beta']).max() <= 2e-7 * sp['f_beta'].max()
 dist.barrier(); dist.destroy_process_group()
 print('rank', rank, 'ok')
 """

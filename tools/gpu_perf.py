@@ -20,6 +20,7 @@ def main():
     ap.add_argument("--K", type=int, default=50)
     ap.add_argument("--V", type=int, default=10000)
     ap.add_argument("--tag", default=os.environ.get("STM_B200_LIB", "default"))
+    ap.add_argument("--init", default="random", choices=["random", "spectral"])
     ap.add_argument("--heldout", action="store_true", help="also time STM.eval_heldout on the training corpus")
     a = ap.parse_args()
     import torch
@@ -31,9 +32,10 @@ def main():
         ptr, ids, cnt, X = bench.make_corpus(a.docs, a.V, a.K)
         np.savez(cache, ptr=ptr, ids=ids, cnt=cnt, X=X)
     from strutopy_b200 import STM
-    m = STM((ptr, ids, cnt), range(a.V), False, a.K, X, False, 10 ** 9, 0, 0.0, init_type="random",
+    m = STM((ptr, ids, cnt), range(a.V), False, a.K, X, False, 10 ** 9, 0, 0.0, init_type=a.init,
             model_type="STM", device=0)
-    m.beta = bench.random_beta(a.K, a.V)
+    if a.init == "random":
+        m.beta = bench.random_beta(a.K, a.V)
     out = []
     for it in range(a.iters):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

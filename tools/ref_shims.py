@@ -44,6 +44,11 @@ def _nnls_solve_qp(P, q, G=None, h=None, A=None, b=None, lb=None, ub=None, solve
 def install():
     if REFERENCE_SRC not in sys.path:
         sys.path.insert(0, REFERENCE_SRC)
+    # STM.mnreg (stm.py:825) uses csr_matrix.A, removed in SciPy 1.14: give the property back so that the
+    # unmodified method runs (tests/golden/mnreg.npz)
+    import scipy.sparse
+    if not hasattr(scipy.sparse.csr_matrix, "A"):
+        scipy.sparse.csr_matrix.A = property(lambda self: self.toarray())
     if "qpsolvers" not in sys.modules:
         m = types.ModuleType("qpsolvers")
         m.solve_qp = _nnls_solve_qp
