@@ -37,6 +37,15 @@
 #define STM_LOG_NOINLINE 1 // keep log()/exp() slow paths out of line (I-cache footprint)
 #endif
 // development-only switches for time attribution (results are WRONG when any is set)
+#ifndef STM_DCSTEP_INLINE
+#define STM_DCSTEP_INLINE 1   // 1: dcstep inlined at ONE call site on register copies of the dcsrch state (r01 A/B: kernel A 33.4 -> 31.2 ms)
+#endif
+#ifndef STM_LS_REGS
+#define STM_LS_REGS 0         // 1: line-search scalars in registers instead of shared memory (needs a larger register budget)
+#endif
+#ifndef STM_DDIV_INLINE
+#define STM_DDIV_INLINE 0     // 1: fp64 divisions of the line-search code inlined (ILP between independent quotients)
+#endif
 #ifndef STM_DBG_NO_PHI
 #define STM_DBG_NO_PHI 0
 #endif
@@ -53,7 +62,7 @@
 #define STM_DBG_SKIP_DENSE 0
 #endif
 #ifndef STM_BFGS_MAX_THREADS
-#define STM_BFGS_MAX_THREADS 448   // launch bound of kernel A (register budget = 65536 / this)
+#define STM_BFGS_MAX_THREADS 384   // launch bound of kernel A (register budget = 65536 / this): 12 warps x 160 registers, no spills (r01 A/B: 448 -> 384: 31.3 -> 29.3 ms)
 #endif
 #define STM_PRAGMA2_(x) _Pragma(#x)
 #define STM_PRAGMA_(x) STM_PRAGMA2_(x)
@@ -166,13 +175,21 @@ __device__ __forceinline__ double np_sign(double x) {
 
 // IEEE fp64 division / square root kept out of line in the (scalar, warp-uniform) line-search code:
 // each inlined copy is ~25 instructions and the state machine has dozens of them (I-cache footprint).
+#if STM_DDIV_INLINE
+static __device__ __forceinline__ double ddiv(double a, double b) { return a / b; }
+#else
 static __device__ __noinline__ double ddiv(double a, double b) { return a / b; }
+#endif
 static __device__ __noinline__ double dsqrt(double a) { return sqrt(a); }
 
 // MINPACK-2 dcstep — scipy/optimize/_dcsrch.py:502-728.  The four cases share ONE copy of the cubic
 // interpolation arithmetic (theta, s, gamma, r): each case performs exactly the operations of the
 // SciPy source in the same order, only the operands are selected first (instruction footprint).
+#if STM_DCSTEP_INLINE
+static __device__ __forceinline__ void dcstep(double& stx, double& fx, double& dx, double& sty, double& fy,
+#else
 static __device__ __noinline__ void dcstep(double& stx, double& fx, double& dx, double& sty, double& fy,
+#endif
                                     double& dy, double& stp, double fp, double dp, int& brackt,
                                     double stpmin, double stpmax) {
     const double sgnd = np_sign(dp) * np_sign(dx);
@@ -546,7 +563,12 @@ __global__ void __launch_bounds__(STM_BFGS_MAX_THREADS, 1) bfgs_kernel(const Est
     const bool is_tm = warp < P.tm_warps;
     unsigned char* small = smem_raw + (size_t)warp * P.smem_small;
     double* vec = reinterpret_cast<double*>(small);                       // [4][KVS]
+#if STM_LS_REGS
+    LsState S_regs;
+    LsState& S = S_regs;
+#else
     LsState& S = *reinterpret_cast<LsState*>(vec + 4 * KVS);
+#endif
     uint64_t* mbar = reinterpret_cast<uint64_t*>(small + 4 * KVS * 8 + sizeof(LsState));
     unsigned char* tbase = smem_raw + (size_t)nwarps * P.smem_small +
                            (size_t)(is_tm ? 0 : warp - P.tm_warps) * P.smem_per_warp;
@@ -736,7 +758,7 @@ __global__ void __launch_bounds__(STM_BFGS_MAX_THREADS, 1) bfgs_kernel(const Est
         const int maxiter = K1 * 200;
         double alpha = 0.0, f_eval = 0.0, dphi = 0.0;
         int have_cache = 0, have_cache2 = 0;
-        if (lane == 0) {
+        if (STM_LS_REGS || lane == 0) {
             S.old_fval = 0.0; S.old_old_fval = 0.0; S.gnorm = 0.0; S.derphi0 = 0.0; S.f2 = 0.0;
             S.brackt = 0; S.stage = 1; S.w1_it = 0; S.w2_i = 0; S.z_i = 0;
         }
@@ -977,6 +999,27 @@ __global__ void __launch_bounds__(STM_BFGS_MAX_THREADS, 1) bfgs_kernel(const Est
                     start_w2 = 1;
                 } else {
                     double stp = stp_in;
+#if STM_DCSTEP_INLINE
+                    {
+                        // one call site on register copies: the modified function of stage 1
+                        // (scipy/optimize/_dcsrch.py:448-470) only changes the operands
+                        const bool mod = (S.stage == 1 && f <= S.fx && f > ftest);
+                        const double gtest = S.gtest;
+                        double stx = S.stx, sty = S.sty;
+                        double fxm = S.fx, fym = S.fy, gxm = S.gx, gym = S.gy, fm = f, gm = gd;
+                        int brackt = S.brackt;
+                        if (mod) {
+                            fm = f - stp * gtest; fxm = fxm - stx * gtest; fym = fym - sty * gtest;
+                            gm = gd - gtest; gxm = gxm - gtest; gym = gym - gtest;
+                        }
+                        dcstep(stx, fxm, gxm, sty, fym, gym, stp, fm, gm, brackt, S.stmin, S.stmax);
+                        if (mod) {
+                            fxm = fxm + stx * gtest; fym = fym + sty * gtest;
+                            gxm = gxm + gtest; gym = gym + gtest;
+                        }
+                        S.stx = stx; S.sty = sty; S.fx = fxm; S.fy = fym; S.gx = gxm; S.gy = gym; S.brackt = brackt;
+                    }
+#else
                     if (S.stage == 1 && f <= S.fx && f > ftest) {
                         double fm = f - stp * S.gtest, fxm = S.fx - S.stx * S.gtest, fym = S.fy - S.sty * S.gtest;
                         double gm = gd - S.gtest, gxm = S.gx - S.gtest, gym = S.gy - S.gtest;
@@ -986,6 +1029,7 @@ __global__ void __launch_bounds__(STM_BFGS_MAX_THREADS, 1) bfgs_kernel(const Est
                     } else {
                         dcstep(S.stx, S.fx, S.gx, S.sty, S.fy, S.gy, stp, f, gd, S.brackt, S.stmin, S.stmax);
                     }
+#endif
                     if (S.brackt) {
                         if (fabs(S.sty - S.stx) >= 0.66 * S.width1) stp = S.stx + 0.5 * (S.sty - S.stx);
                         S.width1 = S.width;
@@ -1942,7 +1986,7 @@ __global__ void __launch_bounds__(STM_POST_MAX_THREADS, 1) post_group_kernel(con
                             ok = 0;
                         } else {
                             if (gt == 0) dvec[k] = dk;
-                            const double pv = ddiv(1.0, dk);
+                            const double pv = 1.0 / dk;   // inlined: on the sweep's critical path (r01 A/B: 10.4 -> 9.7 ms)
                             if (has_patch) {
                                 double ui[4], upj[4];
 #pragma unroll
