@@ -547,6 +547,8 @@ struct LsState {
 // Kernel A: per-document BFGS (stm.py:536-545 -> scipy.optimize.minimize(method="BFGS")).
 // Writes eta (in place), doc_info = status | nit << 4, doc_nfev.
 template <int KPL, int J>
+// Registers are allocated in groups of 4 warps: 9-12 warps get 168 registers per thread, 13-16 warps only 128
+// (which spills), so 12 warps is the widest configuration without spills (r01 A/B in profiles/r01_tuning_log.md).
 __global__ void __launch_bounds__(STM_BFGS_MAX_THREADS, 1) bfgs_kernel(const EstepParams P) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31;
