@@ -1844,7 +1844,7 @@ __global__ void __launch_bounds__(STM_POST_MAX_THREADS, 1) post_group_kernel(con
                 v1[k] = (k < K) ? th[i] * eu[i] : 0.0;
                 v2[k] = (k < K) ? th[i] : 0.0;
             }
-            if (lane == 0) red[4] = quad;
+            if (lane == 0) { red[4] = quad; red[5] = 0.0; }   // red[5]: "a diagonal entry of H is not positive"
         }
         mbar_wait(mbar, parity);
         parity ^= 1;
@@ -1946,6 +1946,7 @@ __global__ void __launch_bounds__(STM_POST_MAX_THREADS, 1) post_group_kernel(con
                 if (k == r) {
                     h = (h - v3[k] + Nsum * thk) + P.prior[k];
                     Dg[k] = h;
+                    if (!(h > 0.0)) red[5] = 1.0;
                 }
                 Hm[(size_t)r * HS + k] = h;
                 Hm[(size_t)k * HS + r] = h;
@@ -1965,7 +1966,8 @@ __global__ void __launch_bounds__(STM_POST_MAX_THREADS, 1) post_group_kernel(con
                     a[r][c] = (has_patch && i < K1 && j < K1) ? ((i == j) ? Dg[i] : Hm[(size_t)i * HS + j])
                                                               : ((i == j) ? 1.0 : 0.0);
                 }
-            int ok = 1;
+            // a non-positive diagonal entry already decides the first PD test (stm.py:1017): no sweep needed
+            int ok = (attempt == 0 && red[5] != 0.0) ? 0 : 1;
 #pragma unroll 1
             for (int kb = 0; 4 * kb < K1 && ok; ++kb) {
 #pragma unroll
