@@ -40,6 +40,9 @@
 #ifndef STM_DCSTEP_INLINE
 #define STM_DCSTEP_INLINE 1   // 1: dcstep inlined at ONE call site on register copies of the dcsrch state (r01 A/B: kernel A 33.4 -> 31.2 ms)
 #endif
+#ifndef STM_UNIFORM_LS
+#define STM_UNIFORM_LS 1      // 1: make the line-search inputs PROVABLY warp-uniform (redux.sync), so that the scalar
+#endif                        //    state machine compiles to uniform branches without convergence barriers
 #ifndef STM_LS_REGS
 #define STM_LS_REGS 0         // 1: line-search scalars in registers instead of shared memory (needs a larger register budget)
 #endif
@@ -171,6 +174,14 @@ __device__ __forceinline__ double np_clip(double x, double lo, double hi) {
 __device__ __forceinline__ double np_sign(double x) {
     if (isnan(x)) return x;
     return (x > 0.0) ? 1.0 : ((x < 0.0) ? -1.0 : 0.0);
+}
+
+// A value that is identical in every lane, passed through redux.sync so that the compiler's divergence analysis
+// knows it (AND of equal bit patterns is the identity).  Branches on such values need no BSSY/BSYNC scaffolding.
+__device__ __forceinline__ double uniform_f64(double v) {
+    const int hi = (int)__reduce_and_sync(STM_FULL, (unsigned)__double2hiint(v));
+    const int lo = (int)__reduce_and_sync(STM_FULL, (unsigned)__double2loint(v));
+    return __hiloint2double(hi, lo);
 }
 
 // IEEE fp64 division / square root kept out of line in the (scalar, warp-uniform) line-search code:
@@ -552,7 +563,11 @@ template <int KPL, int J>
 __global__ void __launch_bounds__(STM_BFGS_MAX_THREADS, 1) bfgs_kernel(const EstepParams P) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31;
+#if STM_UNIFORM_LS
+    const int warp = __reduce_max_sync(STM_FULL, (int)(threadIdx.x >> 5));   // provably uniform (shared-memory addresses follow)
+#else
     const int warp = threadIdx.x >> 5;
+#endif
     const int K = P.K, K1 = K - 1, TS = P.TS;
     constexpr int KV = KPL * 32;
     constexpr int KVS = KV + 8;  // padded stride of the shared K-vectors (TS <= KV+4, block reads <= KV+6)
@@ -964,6 +979,10 @@ __global__ void __launch_bounds__(STM_BFGS_MAX_THREADS, 1) bfgs_kernel(const Est
             }
 
             // ---------------- consume the evaluation --------------------------------------------
+#if STM_UNIFORM_LS
+            f_eval = uniform_f64(f_eval);
+            dphi = uniform_f64(dphi);
+#endif
             STM_T(t_ev1);
             STM_TACC(1, t_ev0, t_ev1);      // slot 1: evaluation (incl. memo check)
             int accept = 0;      // 1: step alpha accepted (f_eval, gt valid)
