@@ -638,7 +638,11 @@ __global__ void __launch_bounds__(STM_BFGS_MAX_THREADS, 1) bfgs_kernel(const Est
     for (;;) {
         int qi = 0;
         if (lane == 0) qi = (int)atomicAdd(P.queue, 1u);
+#if STM_UNIFORM_LS
+        qi = __reduce_max_sync(STM_FULL, qi);   // lanes != 0 hold 0: a provably uniform broadcast (document index, length, loop bounds follow)
+#else
         qi = __shfl_sync(STM_FULL, qi, 0);
+#endif
         if (qi >= P.n_docs) break;
         STM_T(t_doc0);
         const int d = P.docs[qi];
