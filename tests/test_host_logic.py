@@ -174,3 +174,48 @@ def test_two_rank_allreduce_gloo(tmp_path):
     for pr in procs:
         out, _ = pr.communicate(timeout=240)
         assert pr.returncode == 0, out
+
+
+def test_new_fronts_fail_loudly_without_gpu():
+    """spectral_init / sample_corpus / eval_heldout have no CPU fallback either."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from strutopy_b200.generate_docs import sample_corpus
+    from strutopy_b200.spectral import spectral_init
+    docs = (np.array([0, 2, 4]), np.array([0, 1, 0, 1], np.int32), np.array([1.0, 2.0, 2.0, 1.0]))
+    with pytest.raises(RuntimeError):
+        spectral_init(docs, 2, 2)
+    with pytest.raises(RuntimeError):
+        sample_corpus(np.full((3, 2), 0.5), np.full((2, 5), 0.2), 10)
+
+
+def test_spectral_gram_statistics_add_over_shards():
+    """What stm_spectral_gram all-reduces: Htilde'Htilde and diag(Hhat) are sums over documents, so the shards'
+    statistics add up to the global ones and Q = sum - diag(sum) is the unsharded Q (stm.py:134-149)."""
+    from oracle import spectral_numpy as sn
+    ptr, ids, cnt, _, _ = synthetic_corpus(300, 200, 4, n_words=50, seed=5)
+    wprob = sn.word_prob(ptr, ids, cnt)
+    keep = sn.keep_order(wprob, 60)
+    M = sn.dense_dtm(ptr, ids, cnt, width=len(wprob))[:, keep]
+
+    def parts(Ms):
+        wc = Ms.sum(axis=1, keepdims=True)
+        div = wc * (wc - 1)
+        Ht = Ms / np.sqrt(div)
+        return Ht.T @ Ht, np.sum(Ms / div, axis=0)
+
+    g_all, h_all = parts(M)
+    g1, h1 = parts(M[:130])
+    g2, h2 = parts(M[130:])
+    np.testing.assert_allclose(g1 + g2, g_all, rtol=1e-12, atol=1e-15)
+    np.testing.assert_allclose(h1 + h2, h_all, rtol=1e-12, atol=1e-15)
+    np.testing.assert_allclose((g1 + g2) - np.diag(h1 + h2), sn.gram(M), rtol=1e-11, atol=1e-14)
+
+
+def test_first_appearance_renumbering():
+    """generate_docs.py:299-315: ids are renumbered in order of first appearance"""
+    from strutopy_b200.generate_docs import renumber_by_first_appearance
+    new, old_of_new = renumber_by_first_appearance(np.array([7, 3, 7, 9, 3, 0, 9], np.int32))
+    np.testing.assert_array_equal(new, [0, 1, 0, 2, 1, 3, 2])
+    np.testing.assert_array_equal(old_of_new, [7, 3, 9, 0])
