@@ -72,6 +72,7 @@ struct stm_ctx {
     cusolverDnHandle_t cusolver = nullptr;
     int64_t launches = 0;
     cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};   // E-step phases: before kernel A, between, after kernel B
+    cudaStream_t copy_stream = nullptr;                // host API: eta goes home while kernel B runs
     std::string err;
 };
 
@@ -652,6 +653,7 @@ int stm_create(int device, int K, int V, int A, stm_ctx** out) {
     if (c->potrf_lwork < 1) c->potrf_lwork = 1;
     cudaMalloc(&c->d_potrf_work, sizeof(double) * c->potrf_lwork);
     for (int i = 0; i < 3; ++i) cudaEventCreate(&c->ev[i]);
+    cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking);
     *out = c;
     return STM_OK;
 }
@@ -664,6 +666,7 @@ void stm_destroy(stm_ctx* c) {
     if (c->cublas) cublasDestroy(c->cublas);
     if (c->cusolver) cusolverDnDestroy(c->cusolver);
     for (int i = 0; i < 3; ++i) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
+    if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
     delete c;
 }
 
@@ -1075,9 +1078,11 @@ int stm_estep_host(stm_ctx* ctx, const double* beta, const double* mu, const dou
     rc = stm_estep(ctx, ctx->h_beta_t, ctx->h_mu, ctx->h_prior, ctx->h_eta, ctx->h_theta, ctx->h_stats,
                    ctx->h_doc_bound, ctx->h_doc_info, ctx->h_doc_nfev, st);
     if (rc) return rc;
+    // eta is final once kernel A is done (event ev[1]): copy it out on a second stream while kernel B runs
+    CU(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev[1], 0));
+    CU(cudaMemcpyAsync(eta, ctx->h_eta, sizeof(double) * D * K1, cudaMemcpyDeviceToHost, ctx->copy_stream));
     rc = stm_wordmajor_to_kv(ctx, ctx->h_stats + off[0], ctx->h_bss_kv, st);
     if (rc) return rc;
-    CU(cudaMemcpyAsync(eta, ctx->h_eta, sizeof(double) * D * K1, cudaMemcpyDeviceToHost, st));
     CU(cudaMemcpyAsync(theta, ctx->h_theta, sizeof(double) * D * K, cudaMemcpyDeviceToHost, st));
     CU(cudaMemcpyAsync(beta_ss, ctx->h_bss_kv, sizeof(double) * (size_t)A * K * V, cudaMemcpyDeviceToHost, st));
     CU(cudaMemcpyAsync(sigma_ss, ctx->h_stats + off[1], sizeof(double) * K1 * K1, cudaMemcpyDeviceToHost, st));
@@ -1102,6 +1107,7 @@ int stm_estep_host(stm_ctx* ctx, const double* beta, const double* mu, const dou
         }
     }
     CU(cudaStreamSynchronize(st));
+    CU(cudaStreamSynchronize(ctx->copy_stream));
     return STM_OK;
 }
 
