@@ -1976,6 +1976,22 @@ __global__ void __launch_bounds__(STM_POST_MAX_THREADS, 1) post_group_kernel(con
             }
         }
         group_bar(grp);
+        // A 2x2 principal minor that is negative by a clear margin (H_ij^2 > H_ii H_jj) also decides the first
+        // PD test without a sweep: in the spectral-init state ~90 % of the documents fail that test, on average
+        // two thirds of the way through the pivots (measured on the oracle).  Margin 1e-10: anything closer
+        // is left to the pivots.
+        if (red[5] == 0.0) {
+            bool neg = false;
+            for (int r = wg; r < K1; r += POST_GW) {
+                const double dr = Dg[r] * (1.0 + 1e-10);
+                for (int k = lane; k < r; k += 32) {
+                    const double h = Hm[(size_t)r * HS + k];
+                    neg |= (h * h > dr * Dg[k]);
+                }
+            }
+            if (neg) red[5] = 1.0;
+        }
+        group_bar(grp);
 
         // ---- PD test + repairs (stm.py:1017-1021, 1039-1048) and the inverse, by sweeping ----------
         int repair = 0, upper = 0, dead = 0;
