@@ -37,17 +37,32 @@ cudaError_t STM_CAT(stm_launch_post_kpl, STM_KPL)(const stm::EstepParams& P, int
     return cudaGetLastError();
 }
 
-// group version of kernel B (3 warps per document, K-1 <= 52); only instantiated where it applies
-cudaError_t STM_CAT(stm_launch_post_group_kpl, STM_KPL)(const stm::EstepParams& P, int grid, int block, size_t smem,
-                                                        cudaStream_t st) {
+// group version of kernel B (GW warps per document, one 4x4 patch of the lower triangle per thread):
+// the (KPL, GW) pairs that occur — K-1 <= 52: GW 3; K-1 <= 63: 5; K <= 96: 10; K-1 <= 100: 11; K <= 128: 17
+cudaError_t STM_CAT(stm_launch_post_group_kpl, STM_KPL)(const stm::EstepParams& P, int gw, int grid, int block,
+                                                        size_t smem, cudaStream_t st) {
+#define STM_LAUNCH_G(GW)                                                                               \
+    if (gw == GW) {                                                                                    \
+        cudaError_t e = cudaFuncSetAttribute(stm::post_group_kernel<STM_KPL, GW>,                      \
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);  \
+        if (e != cudaSuccess) return e;                                                                \
+        stm::post_group_kernel<STM_KPL, GW><<<grid, block, smem, st>>>(P);                             \
+        return cudaGetLastError();                                                                     \
+    }
 #if STM_KPL <= 2
-    cudaError_t e = cudaFuncSetAttribute(stm::post_group_kernel<STM_KPL>,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    stm::post_group_kernel<STM_KPL><<<grid, block, smem, st>>>(P);
-    return cudaGetLastError();
-#else
+    STM_LAUNCH_G(3)
+#endif
+#if STM_KPL == 2
+    STM_LAUNCH_G(5)
+#endif
+#if STM_KPL == 3
+    STM_LAUNCH_G(10)
+#endif
+#if STM_KPL == 4
+    STM_LAUNCH_G(11)
+    STM_LAUNCH_G(17)
+#endif
+#undef STM_LAUNCH_G
     (void)P; (void)grid; (void)block; (void)smem; (void)st;
     return cudaErrorNotSupported;
-#endif
 }

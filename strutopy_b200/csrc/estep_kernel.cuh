@@ -1689,24 +1689,36 @@ __global__ void __launch_bounds__(256, 1) post_kernel(const EstepParams P) {
 //     pivot k equals the Cholesky pivot L_kk^2, so "np.linalg.cholesky succeeds" (stm.py:1017, 1040)
 //     is "all pivots > 0" and sum log L_ii = 1/2 sum log d_k;
 //   * nu leaves the registers as fp64 reductions into the replicated sigma_ss accumulators.
-constexpr int POST_GW = 3;              // warps per document
-constexpr int POST_GT = POST_GW * 32;   // threads per document
-constexpr int POST_NPATCH = 91;         // 4x4 patches of the lower triangle of a 52x52 matrix
-constexpr int POST_UST = 56;            // stride of the small fp64 vectors (Dg, u, d)
+// Group geometry.  GW warps (GT = 32 GW threads) per document, one 4x4 patch of the lower triangle per thread:
+// nb4 = ceil((K-1)/4) block rows -> nb4 (nb4+1)/2 patches.  K-1 <= 52: 91 patches, GW = 3 (the C3 shape);
+// K-1 <= 63: 136 patches, GW = 5; K <= 96: 300 patches, GW = 10; K-1 <= 100: 325, GW = 11; K <= 128: 528, GW = 17.
+constexpr int POST_GW = 3;              // warps per document of the base configuration (host code: stm::POST_GT)
+constexpr int POST_GT = POST_GW * 32;
+__host__ __device__ constexpr int post_ust(int GW) {        // stride of the small fp64 vectors (Dg, u, d): >= 4 nb4
+    return GW == 3 ? 56 : (GW == 5 ? 72 : (GW <= 11 ? 104 : 136));
+}
 #ifndef STM_POST_MAX_THREADS
 #define STM_POST_MAX_THREADS 576        // 6 groups of 96 threads -> 112 registers per thread
 #endif
-
-__device__ __forceinline__ void group_bar(int grp) {
-    asm volatile("bar.sync %0, %1;" ::"r"(grp + 1), "r"(POST_GT) : "memory");
+__host__ __device__ constexpr int post_group_max_threads(int GW) {   // launch bound: groups x GT
+    return GW == 3 ? STM_POST_MAX_THREADS : (GW == 5 ? 480 : GW * 32);
 }
-// sum over the 96 threads of a group; red = 4 doubles of group-private shared memory
+constexpr int POST_RED = 24;            // doubles of per-group reduction scratch (partials 0..GW-1, scalars 20..)
+
+template <int GW>
+__device__ __forceinline__ void group_bar(int grp) {
+    asm volatile("bar.sync %0, %1;" ::"r"(grp + 1), "r"(GW * 32) : "memory");
+}
+// sum over the threads of a group, partials added in warp order; red = group-private shared memory
+template <int GW>
 __device__ __forceinline__ double group_sum(double v, double* red, int wg, int lane, int grp) {
     v = warp_sum(v);
     if (lane == 0) red[wg] = v;
-    group_bar(grp);
-    const double r = (red[0] + red[1]) + red[2];
-    group_bar(grp);
+    group_bar<GW>(grp);
+    double r = (red[0] + red[1]) + red[2];
+#pragma unroll
+    for (int w = 3; w < GW; ++w) r += red[w];
+    group_bar<GW>(grp);
     return r;
 }
 
@@ -1741,8 +1753,26 @@ __device__ __forceinline__ void hess_row_pass(const float* tile, int TS, int n, 
     }
 }
 
-template <int KPL>
-__global__ void __launch_bounds__(STM_POST_MAX_THREADS, 1) post_group_kernel(const EstepParams P) {
+// row-block dispatch for more than 8 block rows (K > 64): compile-time recursion instead of a switch
+template <int NBMAX, int BR>
+struct HessDispatch {
+    static __device__ __forceinline__ void run(int br, const float* tile, int TS, int n, const double* wv,
+                                               const double* wv2, const int* wid, const double (&ek)[NBMAX], double ekb,
+                                               bool kok, double* ssb, int w4, int kk, double (&acc)[NBMAX][2], double& rs) {
+        if (br == BR) hess_row_pass<NBMAX, BR>(tile, TS, n, wv, wv2, wid, ek, ekb, kok, ssb, w4, kk, acc, rs);
+        else HessDispatch<NBMAX, BR - 1>::run(br, tile, TS, n, wv, wv2, wid, ek, ekb, kok, ssb, w4, kk, acc, rs);
+    }
+};
+template <int NBMAX>
+struct HessDispatch<NBMAX, -1> {
+    static __device__ __forceinline__ void run(int, const float*, int, int, const double*, const double*, const int*,
+                                               const double (&)[NBMAX], double, bool, double*, int, int,
+                                               double (&)[NBMAX][2], double&) {}
+};
+
+template <int KPL, int GW>
+__global__ void __launch_bounds__(post_group_max_threads(GW), 1) post_group_kernel(const EstepParams P) {
+    constexpr int POST_GW = GW, POST_GT = GW * 32, POST_UST = post_ust(GW);
     extern __shared__ __align__(128) unsigned char smem_raw[];
     // warp-uniform indices go through redux.sync so that the compiler KNOWS they are uniform (no
     // reconvergence scaffolding around the warp-synchronous instructions they guard)
@@ -1773,8 +1803,8 @@ __global__ void __launch_bounds__(STM_POST_MAX_THREADS, 1) post_group_kernel(con
     double* ubuf = wv + POST_UST;         //   diagonal, 2 pivot vectors, pivots
     double* dvec = wv + 3 * POST_UST;
     double* vec = reinterpret_cast<double*>(base + tile_bytes + w_bytes);   // [4][KVS]
-    double* red = vec + 4 * KVS;                                            // [8] reductions / scalars
-    float* cw = reinterpret_cast<float*>(red + 8);
+    double* red = vec + 4 * KVS;                                            // [POST_RED] reductions / scalars
+    float* cw = reinterpret_cast<float*>(red + POST_RED);
     int* wid = reinterpret_cast<int*>(cw + P.n_cap);
     uint64_t* mbar = reinterpret_cast<uint64_t*>(wid + ((P.n_cap + 1) & ~1));
     int* qslot = reinterpret_cast<int*>(mbar + 1);
@@ -1785,7 +1815,7 @@ __global__ void __launch_bounds__(STM_POST_MAX_THREADS, 1) post_group_kernel(con
     for (int i = gt; i < 4 * KVS; i += POST_GT) vec[i] = 0.0;
     if (gt == 0) mbar_init(mbar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    group_bar(grp);
+    group_bar<GW>(grp);
     uint32_t parity = 0;
 
     const int ggrp = blockIdx.x * (blockDim.x / POST_GT) + grp;
@@ -1793,7 +1823,8 @@ __global__ void __launch_bounds__(STM_POST_MAX_THREADS, 1) post_group_kernel(con
     double* sig_acc = P.sigma_ss_rep + (size_t)(ggrp % P.n_rep) * K1 * K1;
 
     // this thread's 4x4 patch of the lower triangle
-    const bool has_patch = gt < POST_NPATCH;
+    const int nb4 = (K1 + 3) >> 2;
+    const bool has_patch = gt < nb4 * (nb4 + 1) / 2;
     int pi = 0, pj = 0;
     if (has_patch) {
         while ((pi + 1) * (pi + 2) / 2 <= gt) pi++;
@@ -1810,7 +1841,7 @@ __global__ void __launch_bounds__(STM_POST_MAX_THREADS, 1) post_group_kernel(con
     for (;;) {
         if (gt == 0) *qslot = (int)atomicAdd(P.queue, 1u);
         fence_proxy_async();   // the previous document's generic smem accesses precede the async writes
-        group_bar(grp);
+        group_bar<GW>(grp);
         const int qi = __reduce_max_sync(STM_FULL, *qslot);
         if (qi >= P.n_docs) break;
         const int d = P.docs[qi];
@@ -1832,7 +1863,7 @@ __global__ void __launch_bounds__(STM_POST_MAX_THREADS, 1) post_group_kernel(con
             tma_row_g2s(tile + (size_t)v * TS, beta_a + (size_t)w * TS, (uint32_t)(TS * 4), mbar);
         }
         if (gt < 8) tile[(size_t)n * TS + gt] = 0.f;   // what the last word's last topic block over-reads
-        const double Nsum = group_sum(nsum_l, red, wg, lane, grp);   // np.sum(word_count)
+        const double Nsum = group_sum<GW>(nsum_l, red, wg, lane, grp);   // np.sum(word_count)
 
         // ---- theta (stm.py:546-549, 905-909) and the prior quadratic, by the group's first warp ---
         double th[KPL];
@@ -1867,11 +1898,11 @@ __global__ void __launch_bounds__(STM_POST_MAX_THREADS, 1) post_group_kernel(con
                 v1[k] = (k < K) ? th[i] * eu[i] : 0.0;
                 v2[k] = (k < K) ? th[i] : 0.0;
             }
-            if (lane == 0) { red[4] = quad; red[5] = 0.0; }   // red[5]: "a diagonal entry of H is not positive"
+            if (lane == 0) { red[20] = quad; red[21] = 0.0; }   // red[21]: "the first PD test is already decided"
         }
         mbar_wait(mbar, parity);
         parity ^= 1;
-        group_bar(grp);
+        group_bar<GW>(grp);
 
         // ---- colsum_v = sum_k e_k beta_kv, log-likelihood part of the bound (stm.py:1088-1096) ----
         double loglik;
@@ -1902,7 +1933,7 @@ __global__ void __launch_bounds__(STM_POST_MAX_THREADS, 1) post_group_kernel(con
                 wv2[v] = sq;
             }
             if (gt < 4) wv[n + gt] = 0.0;
-            loglik = group_sum(logprod_value(lp), red, wg, lane, grp);   // also publishes wv / wv2
+            loglik = group_sum<GW>(logprod_value(lp), red, wg, lane, grp);   // also publishes wv / wv2
         }
 
         // ---- Hessian data term sum_v b_v b_v' (stm.py:1000-1006) on the fp64 tensor cores (DMMA
@@ -1927,19 +1958,23 @@ __global__ void __launch_bounds__(STM_POST_MAX_THREADS, 1) post_group_kernel(con
                 const double ekb = v0[kb];
                 const bool kok = kb < K;
                 double* ssb = beta_ss_a + kb;
-                switch (br) {
-                    case 0: hess_row_pass<NBMAX, 0>(tile, TS, n, wv, wv2, wid, ek, ekb, kok, ssb, w4, kk, acc, rs); break;
-                    case 1: hess_row_pass<NBMAX, 1>(tile, TS, n, wv, wv2, wid, ek, ekb, kok, ssb, w4, kk, acc, rs); break;
-                    case 2: hess_row_pass<NBMAX, 2>(tile, TS, n, wv, wv2, wid, ek, ekb, kok, ssb, w4, kk, acc, rs); break;
-                    case 3: hess_row_pass<NBMAX, 3>(tile, TS, n, wv, wv2, wid, ek, ekb, kok, ssb, w4, kk, acc, rs); break;
-                    default:
-                        if constexpr (NBMAX > 4) {
-                            if (br == 4) hess_row_pass<NBMAX, 4>(tile, TS, n, wv, wv2, wid, ek, ekb, kok, ssb, w4, kk, acc, rs);
-                            else if (br == 5) hess_row_pass<NBMAX, 5>(tile, TS, n, wv, wv2, wid, ek, ekb, kok, ssb, w4, kk, acc, rs);
-                            else if (br == 6) hess_row_pass<NBMAX, 6>(tile, TS, n, wv, wv2, wid, ek, ekb, kok, ssb, w4, kk, acc, rs);
-                            else hess_row_pass<NBMAX, 7>(tile, TS, n, wv, wv2, wid, ek, ekb, kok, ssb, w4, kk, acc, rs);
-                        }
-                        break;
+                if constexpr (NBMAX > 8) {
+                    HessDispatch<NBMAX, NBMAX - 1>::run(br, tile, TS, n, wv, wv2, wid, ek, ekb, kok, ssb, w4, kk, acc, rs);
+                } else {
+                    switch (br) {
+                        case 0: hess_row_pass<NBMAX, 0>(tile, TS, n, wv, wv2, wid, ek, ekb, kok, ssb, w4, kk, acc, rs); break;
+                        case 1: hess_row_pass<NBMAX, 1>(tile, TS, n, wv, wv2, wid, ek, ekb, kok, ssb, w4, kk, acc, rs); break;
+                        case 2: hess_row_pass<NBMAX, 2>(tile, TS, n, wv, wv2, wid, ek, ekb, kok, ssb, w4, kk, acc, rs); break;
+                        case 3: hess_row_pass<NBMAX, 3>(tile, TS, n, wv, wv2, wid, ek, ekb, kok, ssb, w4, kk, acc, rs); break;
+                        default:
+                            if constexpr (NBMAX > 4) {
+                                if (br == 4) hess_row_pass<NBMAX, 4>(tile, TS, n, wv, wv2, wid, ek, ekb, kok, ssb, w4, kk, acc, rs);
+                                else if (br == 5) hess_row_pass<NBMAX, 5>(tile, TS, n, wv, wv2, wid, ek, ekb, kok, ssb, w4, kk, acc, rs);
+                                else if (br == 6) hess_row_pass<NBMAX, 6>(tile, TS, n, wv, wv2, wid, ek, ekb, kok, ssb, w4, kk, acc, rs);
+                                else hess_row_pass<NBMAX, 7>(tile, TS, n, wv, wv2, wid, ek, ekb, kok, ssb, w4, kk, acc, rs);
+                            }
+                            break;
+                    }
                 }
                 // C fragment: row = lane>>2, cols = 2*(lane&3) + {0,1}
                 const int gi = br * 8 + kk;
@@ -1958,7 +1993,7 @@ __global__ void __launch_bounds__(STM_POST_MAX_THREADS, 1) post_group_kernel(con
                 if (w4 == 0 && kb < KV) v3[kb] = rs;
             }
         }
-        group_bar(grp);   // tile dead; Hg and v3 complete
+        group_bar<GW>(grp);   // tile dead; Hg and v3 complete
 
         // ---- assemble H = data - N theta theta' + diag(-rowsum + N theta) + siginv (stm.py:1007-1015)
         for (int r = wg; r < K1; r += POST_GW) {
@@ -1969,18 +2004,18 @@ __global__ void __launch_bounds__(STM_POST_MAX_THREADS, 1) post_group_kernel(con
                 if (k == r) {
                     h = (h - v3[k] + Nsum * thk) + P.prior[k];
                     Dg[k] = h;
-                    if (!(h > 0.0)) red[5] = 1.0;
+                    if (!(h > 0.0)) red[21] = 1.0;
                 }
                 Hm[(size_t)r * HS + k] = h;
                 Hm[(size_t)k * HS + r] = h;
             }
         }
-        group_bar(grp);
+        group_bar<GW>(grp);
         // A 2x2 principal minor that is negative by a clear margin (H_ij^2 > H_ii H_jj) also decides the first
         // PD test without a sweep: in the spectral-init state ~90 % of the documents fail that test, on average
         // two thirds of the way through the pivots (measured on the oracle).  Margin 1e-10: anything closer
         // is left to the pivots.
-        if (red[5] == 0.0) {
+        if (red[21] == 0.0) {
             bool neg = false;
             for (int r = wg; r < K1; r += POST_GW) {
                 const double dr = Dg[r] * (1.0 + 1e-10);
@@ -1989,9 +2024,9 @@ __global__ void __launch_bounds__(STM_POST_MAX_THREADS, 1) post_group_kernel(con
                     neg |= (h * h > dr * Dg[k]);
                 }
             }
-            if (neg) red[5] = 1.0;
+            if (neg) red[21] = 1.0;
         }
-        group_bar(grp);
+        group_bar<GW>(grp);
 
         // ---- PD test + repairs (stm.py:1017-1021, 1039-1048) and the inverse, by sweeping ----------
         int repair = 0, upper = 0, dead = 0;
@@ -2006,7 +2041,7 @@ __global__ void __launch_bounds__(STM_POST_MAX_THREADS, 1) post_group_kernel(con
                                                               : ((i == j) ? 1.0 : 0.0);
                 }
             // a non-positive diagonal entry already decides the first PD test (stm.py:1017): no sweep needed
-            int ok = (attempt == 0 && red[5] != 0.0) ? 0 : 1;
+            int ok = (attempt == 0 && red[21] != 0.0) ? 0 : 1;
 #pragma unroll 1
             for (int kb = 0; 4 * kb < K1 && ok; ++kb) {
 #pragma unroll
@@ -2023,7 +2058,7 @@ __global__ void __launch_bounds__(STM_POST_MAX_THREADS, 1) post_group_kernel(con
                                 for (int r = 0; r < 4; ++r) ub[4 * pi + r] = a[r][kr];
                             }
                         }
-                        group_bar(grp);
+                        group_bar<GW>(grp);
                         const double dk = ub[k];
                         if (!(dk > 0.0)) {
                             ok = 0;
@@ -2053,7 +2088,7 @@ __global__ void __launch_bounds__(STM_POST_MAX_THREADS, 1) post_group_kernel(con
                 }
             }
             if (ok) break;
-            group_bar(grp);   // every thread has left the sweep before Dg changes
+            group_bar<GW>(grp);   // every thread has left the sweep before Dg changes
             if (attempt == 0 || attempt == 2 || attempt == 3) {
                 // make_pd (stm.py:964-984): d_i <- max(d_i, sum_j!=i |H_ij|)
                 for (int i = gt; i < K1; i += POST_GT) {
@@ -2072,16 +2107,16 @@ __global__ void __launch_bounds__(STM_POST_MAX_THREADS, 1) post_group_kernel(con
             else if (attempt == 2) repair += 4;      // decompose_hessian(): make_pd
             else if (attempt == 3) { repair += 8; upper = 1; }  // scipy.linalg.cholesky (upper) of make_pd + 1e-5 I
             else { dead = 1; break; }
-            group_bar(grp);
+            group_bar<GW>(grp);
         }
-        group_bar(grp);   // dvec complete
+        group_bar<GW>(grp);   // dvec complete
 
         // ---- bound (stm.py:1085-1100): sum log L_ii = 1/2 sum log d_k ------------------------------
         double lg = 0.0;
         if (gt < K1) lg = dead ? nan("") : log_noinline(dvec[gt]);
-        const double logdet_half = 0.5 * group_sum(lg, red, wg, lane, grp);
+        const double logdet_half = 0.5 * group_sum<GW>(lg, red, wg, lane, grp);
         if (gt == 0) {
-            P.doc_bound[d] = loglik - logdet_half - 0.5 * red[4] - sigmaentropy;
+            P.doc_bound[d] = loglik - logdet_half - 0.5 * red[20] - sigmaentropy;
             P.doc_info[d] = (P.doc_info[d] & 0xffffff) | (repair << 24);
         }
         // ---- nu = H^-1 (stm.py:1052-1066, accumulated stm.py:582): the swept matrix is -H^-1 --------

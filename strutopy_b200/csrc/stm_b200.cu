@@ -28,7 +28,8 @@ struct LengthClass {
     int warps = 0, smem_per_warp = 0, grid = 0;
     int smem_small = 0, tm_warps = 0, tm_cols = 0;   // kernel A: small block bytes, TMEM-resident warps / columns each
     int post_warps = 0, post_smem_per_warp = 0, post_grid = 0;
-    int post_groups = 0;   // > 0: group version of kernel B (3 warps per document), this many documents per CTA
+    int post_groups = 0;   // > 0: group version of kernel B, this many documents per CTA
+    int post_gw = 3;       //      warps per document there
 };
 
 }  // namespace
@@ -134,17 +135,25 @@ size_t post_smem_per_warp(int n_cap, int TS, int K1, int KPL) {
 }
 
 // mirrors the carve-up at the top of stm::post_group_kernel
-size_t post_group_smem(int n_cap, int TS, int K1, int KPL) {
+size_t post_group_smem(int n_cap, int TS, int K1, int KPL, int gw) {
     const int HS = K1 | 1;
     size_t tile = (size_t)(n_cap + 1) * TS * 4;
     const size_t hb = (size_t)K1 * HS * 8;
     if (hb > tile) tile = hb;
     tile = (tile + 127) & ~(size_t)127;
     size_t wb = (size_t)(n_cap + 4) * 16;
-    if (wb < (size_t)4 * stm::POST_UST * 8) wb = (size_t)4 * stm::POST_UST * 8;
+    if (wb < (size_t)4 * stm::post_ust(gw) * 8) wb = (size_t)4 * stm::post_ust(gw) * 8;
     const int KVS = KPL * 32 + 8;
-    const size_t total = tile + wb + (size_t)4 * KVS * 8 + 64 + (size_t)n_cap * 4 + (size_t)((n_cap + 1) & ~1) * 4 + 16;
+    const size_t total = tile + wb + (size_t)4 * KVS * 8 + (size_t)stm::POST_RED * 8 + (size_t)n_cap * 4 +
+                         (size_t)((n_cap + 1) & ~1) * 4 + 16;
     return (total + 127) & ~(size_t)127;
+}
+// warps per document of the group version of kernel B (one 4x4 patch of the lower triangle per thread)
+int post_group_warps(int K1, int KPL) {
+    if (K1 <= 52) return 3;
+    if (KPL == 2) return 5;
+    if (KPL == 3) return 10;
+    return K1 <= 100 ? 11 : 17;
 }
 
 }  // namespace
@@ -158,8 +167,10 @@ cudaError_t stm_launch_post_kpl1(const stm::EstepParams&, int, int, size_t, cuda
 cudaError_t stm_launch_post_kpl2(const stm::EstepParams&, int, int, size_t, cudaStream_t);
 cudaError_t stm_launch_post_kpl3(const stm::EstepParams&, int, int, size_t, cudaStream_t);
 cudaError_t stm_launch_post_kpl4(const stm::EstepParams&, int, int, size_t, cudaStream_t);
-cudaError_t stm_launch_post_group_kpl1(const stm::EstepParams&, int, int, size_t, cudaStream_t);
-cudaError_t stm_launch_post_group_kpl2(const stm::EstepParams&, int, int, size_t, cudaStream_t);
+cudaError_t stm_launch_post_group_kpl1(const stm::EstepParams&, int, int, int, size_t, cudaStream_t);
+cudaError_t stm_launch_post_group_kpl2(const stm::EstepParams&, int, int, int, size_t, cudaStream_t);
+cudaError_t stm_launch_post_group_kpl3(const stm::EstepParams&, int, int, int, size_t, cudaStream_t);
+cudaError_t stm_launch_post_group_kpl4(const stm::EstepParams&, int, int, int, size_t, cudaStream_t);
 namespace {
 
 cudaError_t launch_bfgs(int KPL, const stm::EstepParams& P, int J, int grid, int block, size_t smem,
@@ -750,11 +761,13 @@ int stm_set_corpus(stm_ctx* ctx, int64_t D, const int64_t* doc_ptr, const int32_
                             " bytes) does not fit in shared memory");
         lc.grid = std::min(ctx->sm_count, (lc.n_docs + lc.warps - 1) / lc.warps);
         lc.post_grid = std::min(ctx->sm_count, (lc.n_docs + lc.post_warps - 1) / lc.post_warps);
-        if (ctx->K1 <= 52 && ctx->KPL <= 2 && !getenv("STM_NO_POST_GROUPS")) {
-            const int per_group = (int)post_group_smem(lc.n_cap, ctx->TS, ctx->K1, ctx->KPL);
-            const int g = std::min(STM_POST_MAX_THREADS / stm::POST_GT, ctx->max_smem / per_group);
+        if (!getenv("STM_NO_POST_GROUPS")) {
+            const int gw = post_group_warps(ctx->K1, ctx->KPL);
+            const int per_group = (int)post_group_smem(lc.n_cap, ctx->TS, ctx->K1, ctx->KPL, gw);
+            const int g = std::min(stm::post_group_max_threads(gw) / (32 * gw), ctx->max_smem / per_group);
             if (g >= 1) {
                 lc.post_groups = g;
+                lc.post_gw = gw;
                 lc.post_smem_per_warp = per_group;
                 lc.post_grid = std::min(ctx->sm_count, (lc.n_docs + g - 1) / g);
                 max_warps = std::max(max_warps, lc.post_grid * g);
@@ -868,9 +881,11 @@ int stm_estep(stm_ctx* ctx, const float* beta_t_dev, const double* mu_dev, const
                 P.smem_per_warp = lc.post_smem_per_warp;
                 if (lc.post_groups > 0) {
                     const size_t smem = (size_t)lc.post_smem_per_warp * lc.post_groups;
-                    const int block = lc.post_groups * stm::POST_GT;
-                    CU(ctx->KPL == 1 ? stm_launch_post_group_kpl1(P, lc.post_grid, block, smem, st)
-                                     : stm_launch_post_group_kpl2(P, lc.post_grid, block, smem, st));
+                    const int block = lc.post_groups * lc.post_gw * 32;
+                    CU(ctx->KPL == 1   ? stm_launch_post_group_kpl1(P, lc.post_gw, lc.post_grid, block, smem, st)
+                       : ctx->KPL == 2 ? stm_launch_post_group_kpl2(P, lc.post_gw, lc.post_grid, block, smem, st)
+                       : ctx->KPL == 3 ? stm_launch_post_group_kpl3(P, lc.post_gw, lc.post_grid, block, smem, st)
+                                       : stm_launch_post_group_kpl4(P, lc.post_gw, lc.post_grid, block, smem, st));
                 } else {
                     CU(launch_post(ctx->KPL, P, lc.post_grid, lc.post_warps * 32,
                                    (size_t)lc.post_smem_per_warp * lc.post_warps, st));
