@@ -1703,6 +1703,9 @@ __host__ __device__ constexpr int post_ust(int GW) {        // stride of the sma
 __host__ __device__ constexpr int post_group_max_threads(int GW) {   // launch bound: groups x GT
     return GW == 3 ? STM_POST_MAX_THREADS : (GW == 5 ? 480 : GW * 32);
 }
+__host__ __device__ constexpr int post_group_min_blocks(int GW) {    // CTAs per SM the register budget is cut for
+    return (GW == 10 || GW == 11) ? 2 : 1;
+}
 constexpr int POST_RED = 24;            // doubles of per-group reduction scratch (partials 0..GW-1, scalars 20..)
 
 template <int GW>
@@ -1771,7 +1774,7 @@ struct HessDispatch<NBMAX, -1> {
 };
 
 template <int KPL, int GW>
-__global__ void __launch_bounds__(post_group_max_threads(GW), 1) post_group_kernel(const EstepParams P) {
+__global__ void __launch_bounds__(post_group_max_threads(GW), post_group_min_blocks(GW)) post_group_kernel(const EstepParams P) {
     constexpr int POST_GW = GW, POST_GT = GW * 32, POST_UST = post_ust(GW);
     extern __shared__ __align__(128) unsigned char smem_raw[];
     // warp-uniform indices go through redux.sync so that the compiler KNOWS they are uniform (no

@@ -769,7 +769,9 @@ int stm_set_corpus(stm_ctx* ctx, int64_t D, const int64_t* doc_ptr, const int32_
                 lc.post_groups = g;
                 lc.post_gw = gw;
                 lc.post_smem_per_warp = per_group;
-                lc.post_grid = std::min(ctx->sm_count, (lc.n_docs + g - 1) / g);
+                // CTAs per SM: what the kernel's register budget was cut for, if the shared memory agrees
+                const int per_sm = std::max(1, std::min(stm::post_group_min_blocks(gw), ctx->max_smem / (per_group * g)));
+                lc.post_grid = std::min(ctx->sm_count * per_sm, (lc.n_docs + g - 1) / g);
                 max_warps = std::max(max_warps, lc.post_grid * g);
             }
         }
