@@ -121,6 +121,32 @@ def test_estep_vs_c_oracle_shapes(lib, D, V, K, nw):
     np.testing.assert_allclose(o["beta_ss"], ref["beta_ss"], rtol=0, atol=1e-5)
 
 
+def test_estep_config5_shape_content_aspects_vs_c_oracle(lib):
+    """BASELINE config 5's shape in small: K=100 (11 warps per document in kernel B), A=2 content aspects
+    (beta_index = d mod 2, aspect-indexed beta gather and beta_ss scatter, stm.py:599-620, 582-590)."""
+    D, V, K, A = 400, 3000, 100, 2
+    ptr, ids, cnt, X, _ = synthetic_corpus(D, V, K, n_words=150, seed=5)
+    rng = np.random.default_rng(5)
+    beta = rng.dirichlet(np.full(V, 0.05), (A, K))
+    beta = np.maximum(beta, 1e-30).astype(np.float32).astype(np.float64)
+    aspect = (np.arange(D) % A).astype(np.int32)
+    siginv, ent = c_oracle.prologue(np.eye(K - 1) * 3.0 + 0.1)
+    mu = rng.normal(0, 0.3, size=(D, K - 1))
+    eta0 = rng.normal(0, 0.3, size=(D, K - 1))
+    ref = c_oracle.estep(ptr, ids, cnt, beta, mu, siginv, ent, eta0, aspect=aspect, nthreads=4)
+    ctx = lib.Context(K, V, A)
+    ctx.set_corpus(ptr, ids, cnt, aspect)
+    o = ctx.estep_host(beta, mu, siginv, ent, eta0)
+    ctx.close()
+    assert abs(o["bound"] - ref["bound"]) <= 1e-9 * abs(ref["bound"])
+    assert np.abs(o["eta"] - ref["eta"]).max() <= 1e-6
+    np.testing.assert_array_equal(o["status"], ref["status"])
+    np.testing.assert_array_equal(o["repair"], ref["repair"])
+    assert o["beta_ss"].shape == (A, K, V)
+    np.testing.assert_allclose(o["beta_ss"], ref["beta_ss"], rtol=0, atol=1e-5)
+    np.testing.assert_allclose(o["sigma_ss"], ref["sigma_ss"], rtol=1e-6, atol=1e-6)
+
+
 def test_edge_cases_empty_ragged_long(lib):
     """empty document, single-word documents, a 300-word and a 700-word document (multi-pass tiles)"""
     K, V = 10, 1500
