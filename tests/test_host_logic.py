@@ -219,3 +219,18 @@ def test_first_appearance_renumbering():
     new, old_of_new = renumber_by_first_appearance(np.array([7, 3, 7, 9, 3, 0, 9], np.int32))
     np.testing.assert_array_equal(new, [0, 1, 0, 2, 1, 3, 2])
     np.testing.assert_array_equal(old_of_new, [7, 3, 9, 0])
+
+
+def test_bench_reference_arm_contract():
+    """`bench.py --impl reference` (the reference's CPU path = the NumPy/SciPy port on host cores) runs without a GPU
+    and prints one JSON line with the keys the driver reads."""
+    import json
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1",
+                          "--warmup", "0", "--ref-docs-per-core", "1"], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr[-2000:]
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["metric"] == "estep_docs_per_sec_K50_V10k" and line["unit"] == "docs/s"
+    assert line["higher_is_better"] is True and line["value"] > 0 and line["steps"] == 1
+    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
+    assert line["e2e"] == {"value": line["value"], "unit": "docs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert "workload" in line["config"]
