@@ -489,15 +489,18 @@ class STM:
         with open(os.path.join(output_dir, "lower_bound.pickle"), "wb") as f:
             pickle.dump(self.last_bounds, f)
 
+    def ecdf(self, arr):
+        """ECDF values of a 1-D array, stm.py:1257-1259"""
+        import scipy.stats
+        return scipy.stats.rankdata(arr, method="max") / arr.size
+
     def frex(self, w=0.5):
         """FREX scores, stm.py:1203-1219"""
         import scipy.special
-        import scipy.stats
         logbeta = np.log(self.beta)
         excl = logbeta - scipy.special.logsumexp(logbeta, axis=0)
-        ecdf = lambda arr: scipy.stats.rankdata(arr, method="max") / arr.size  # noqa: E731
-        excl_ecdf = np.apply_along_axis(ecdf, 1, excl)
-        freq_ecdf = np.apply_along_axis(ecdf, 1, logbeta)
+        excl_ecdf = np.apply_along_axis(self.ecdf, 1, excl)
+        freq_ecdf = np.apply_along_axis(self.ecdf, 1, logbeta)
         return 1.0 / (w / excl_ecdf + (1 - w) / freq_ecdf)
 
     def label_topics(self, topics, n, frexweight=0.5, print_labels=False):

@@ -307,6 +307,30 @@ def test_em_trace_toy_ctm_vs_live_reference():
     np.testing.assert_allclose(np.mean(m.beta.sum(axis=1)), 1.0, atol=1e-4)
 
 
+def test_labelling_helpers_follow_the_reference():
+    """label_topics / frex / find_thoughts / ecdf (stm.py:1151-1259) on a fitted model: same formulas on the host
+    copies of beta / theta the device state produces."""
+    import scipy.special
+    import scipy.stats
+    g = load_golden("estep_K5.npz")
+    K, V = int(g["K"]), int(g["V"])
+    m = _front(g, K, iters=2)
+    m.expectation_maximization(saving=False)
+    lb = np.log(m.beta)
+    ex = lb - scipy.special.logsumexp(lb, axis=0)
+    ec = lambda a: scipy.stats.rankdata(a, method="max") / a.size  # noqa: E731
+    ref = 1.0 / (0.3 / np.apply_along_axis(ec, 1, ex) + 0.7 / np.apply_along_axis(ec, 1, lb))
+    np.testing.assert_allclose(m.frex(w=0.3), ref, rtol=1e-12)
+    np.testing.assert_allclose(m.ecdf(np.array([3.0, 1.0, 2.0, 2.0])), [1.0, 0.25, 0.75, 0.75])
+    prob, frex = m.label_topics(None, 4)
+    assert len(prob) == K and all(len(p) == 4 for p in prob) and len(frex) == K
+    assert prob[2] == [int(i) for i in np.argsort(-m.beta[2])[:4]]       # the "dictionary" is range(V)
+    top = m.find_thoughts([1], n=5)
+    np.testing.assert_array_equal(top, np.argsort(-m.theta[:, 1])[:5])
+    two = m.find_thoughts([0, 3], threshold=0.0, n=3)
+    assert isinstance(two, list) and len(two) == 2 and len(two[1]) == 3
+
+
 def test_random_init_matches_reference_rng():
     g = load_golden("em_c1.npz")
     m = _front(g, int(g["K"]))
