@@ -32,3 +32,51 @@ def pack_corpus(documents):
 def word_counts(ptr, ids, cnt, V):
     """column sums of the document-term matrix (`STM.wcounts`, stm.py:485-486)"""
     return np.bincount(ids, weights=cnt.astype(np.float64), minlength=V)
+
+
+def read_mm(path):
+    """A gensim `MmCorpus` file (Matrix Market coordinate format, documents x words, 1-based; written by
+    `corpora.MmCorpus.serialize`, 02_create_corpus.py:42 — e.g. the reference's artifacts/wiki_data/BoW_corpus.mm,
+    read back at 03_fit_reference_model.py:43-46) -> (doc_ptr, word_id, count, V).  Duplicate (document, word)
+    entries are summed, ids come out ascending within a document."""
+    D = V = nnz = None
+    rows, cols, vals = [], [], []
+    with open(path) as f:
+        header = f.readline()
+        if not header.startswith("%%MatrixMarket") or "coordinate" not in header:
+            raise ValueError("not a Matrix Market coordinate file")
+        for line in f:
+            if line.startswith("%") or not line.strip():
+                continue
+            parts = line.split()
+            if D is None:
+                D, V, nnz = int(parts[0]), int(parts[1]), int(parts[2])
+                continue
+            rows.append(int(parts[0]) - 1)
+            cols.append(int(parts[1]) - 1)
+            vals.append(float(parts[2]))
+    if D is None:
+        raise ValueError("missing size line")
+    rows, cols, vals = np.asarray(rows, np.int64), np.asarray(cols, np.int64), np.asarray(vals, np.float64)
+    if len(rows) != nnz:
+        raise ValueError(f"expected {nnz} entries, found {len(rows)}")
+    if len(rows) and (rows.min() < 0 or rows.max() >= D or cols.min() < 0 or cols.max() >= V):
+        raise ValueError("index out of range")
+    key = rows * V + cols
+    uk, inv = np.unique(key, return_inverse=True)
+    cnt = np.bincount(inv, weights=vals, minlength=len(uk))
+    ptr = np.zeros(D + 1, dtype=np.int64)
+    np.cumsum(np.bincount(uk // V, minlength=D), out=ptr[1:])
+    return ptr, (uk % V).astype(np.int32), cnt.astype(np.float32), V
+
+
+def write_mm(path, doc_ptr, word_id, count, V):
+    """CSR corpus -> the same file format (`MmCorpus.serialize`), so that the reference's scripts can read it."""
+    doc_ptr = np.asarray(doc_ptr, np.int64)
+    D = len(doc_ptr) - 1
+    rows = np.repeat(np.arange(1, D + 1), np.diff(doc_ptr))
+    with open(path, "w") as f:
+        f.write("%%MatrixMarket matrix coordinate real general\n")
+        f.write(f"{D} {int(V)} {len(word_id)}\n")
+        for r, w, c in zip(rows.tolist(), np.asarray(word_id).tolist(), np.asarray(count).tolist()):
+            f.write(f"{r} {w + 1} {int(c) if float(c).is_integer() else repr(float(c))}\n")

@@ -234,3 +234,27 @@ def test_bench_reference_arm_contract():
     assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
     assert line["e2e"] == {"value": line["value"], "unit": "docs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert "workload" in line["config"]
+
+
+def test_matrix_market_corpus_round_trip(tmp_path):
+    """gensim MmCorpus files (02_create_corpus.py:42, 03_fit_reference_model.py:43-46): write -> read gives the CSR
+    back; the reference's own file layout (1-based, "D V nnz" size line, real counts) parses."""
+    from strutopy_b200.corpus import read_mm, write_mm
+    ptr, ids, cnt, _, _ = synthetic_corpus(40, 90, 3, n_words=30, seed=1)
+    path = tmp_path / "BoW_corpus.mm"
+    write_mm(path, ptr, ids, cnt, 90)
+    p2, i2, c2, V = read_mm(path)
+    assert V == 90
+    np.testing.assert_array_equal(p2, ptr)
+    np.testing.assert_array_equal(i2, ids)
+    np.testing.assert_array_equal(c2, cnt)
+    (tmp_path / "ref.mm").write_text("%%MatrixMarket matrix coordinate real general\n2 5 4                \n"
+                                     "1 1 1\n1 3 2\n2 2 1\n2 5 3\n")
+    p3, i3, c3, V3 = read_mm(tmp_path / "ref.mm")
+    assert V3 == 5 and p3.tolist() == [0, 2, 4] and i3.tolist() == [0, 2, 1, 4] and c3.tolist() == [1.0, 2.0, 1.0, 3.0]
+    w = load_golden("wiki_corpus.npz")   # the reference's shipped corpus survives the round trip too
+    write_mm(tmp_path / "wiki.mm", w["doc_ptr"], w["word_id"], w["count"], int(w["V"]))
+    p4, i4, c4, V4 = read_mm(tmp_path / "wiki.mm")
+    np.testing.assert_array_equal(p4, w["doc_ptr"])
+    np.testing.assert_array_equal(i4, w["word_id"])
+    np.testing.assert_array_equal(c4, w["count"].astype(np.float32))
