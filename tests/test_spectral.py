@@ -139,3 +139,23 @@ def test_front_spectral_init_and_fit():
     m.expectation_maximization(saving=False)
     assert len(m.last_bounds) == 3 and np.all(np.isfinite(m.last_bounds))
     assert m.last_bounds[-1] > m.last_bounds[0]
+
+
+@pytest.mark.gpu
+def test_wiki_corpus_from_mm_file_spectral_fit(tmp_path):
+    """INTEGRATION.md's example: the reference's shipped corpus through an MmCorpus file, spectral init, a short fit."""
+    from strutopy_b200 import STM
+    from strutopy_b200.corpus import read_mm, write_mm
+    g, w = load_golden("spectral.npz"), load_golden("wiki_corpus.npz")
+    write_mm(tmp_path / "BoW_corpus.mm", w["doc_ptr"], w["word_id"], w["count"], int(w["V"]))
+    ptr, ids, cnt, V = read_mm(tmp_path / "BoW_corpus.mm")
+    K = int(g["w_cfg"][2])
+    m = STM(documents=(ptr, ids, cnt), dictionary=range(V), X=w["X_50"], K=K, content=False, kappa_interactions=False,
+            max_em_iter=3, sigma_prior=0, convergence_threshold=1e-5, lda_beta=True, init_type="spectral",
+            model_type="STM")
+    ref = g["w_beta_cols"]
+    assert np.abs(m.beta[:, g["w_cols"]] - ref).max() <= 2e-7 * ref.max()      # fp32 storage of beta
+    m.expectation_maximization(saving=False)
+    assert len(m.last_bounds) == 3 and np.all(np.isfinite(m.last_bounds))
+    prob, frex = m.label_topics(None, 5)
+    assert len(prob) == K and all(0 <= i < V for i in prob[0])
