@@ -14,7 +14,8 @@ from conftest import ROOT, load_golden, synthetic_corpus
 from oracle import c_oracle, stm_numpy
 from strutopy_b200 import _lib
 from strutopy_b200.corpus import pack_corpus, word_counts
-from strutopy_b200.parallel import mstep_from_stats, pack_stats, shard_bounds, stats_layout
+from oracle.stats_numpy import mstep_from_stats, pack_stats
+from strutopy_b200.parallel import shard_bounds, stats_layout
 from strutopy_b200.stm import design_matrix
 
 
@@ -136,7 +137,8 @@ import os, sys
 sys.path.insert(0, {root!r}); sys.path.insert(0, os.path.join({root!r}, 'tests'))
 import numpy as np, torch, torch.distributed as dist
 from conftest import load_golden
-from strutopy_b200.parallel import allreduce_stats, shard_bounds, stats_layout, mstep_from_stats
+from strutopy_b200.parallel import allreduce_stats, shard_bounds, stats_layout
+from oracle.stats_numpy import mstep_from_stats
 from test_host_logic import _shard_stats
 dist.init_process_group('gloo', rank=int(os.environ['RANK']), world_size=2)
 g = load_golden('estep_K5.npz'); pfx = 'it2_'
@@ -258,3 +260,26 @@ def test_matrix_market_corpus_round_trip(tmp_path):
     np.testing.assert_array_equal(p4, w["doc_ptr"])
     np.testing.assert_array_equal(i4, w["word_id"])
     np.testing.assert_array_equal(c4, w["count"].astype(np.float32))
+
+
+def test_product_never_touches_the_oracle():
+    """oracle/ is test infrastructure: nothing under strutopy_b200/ may import, link or execute it, and the product
+    must not carry a CPU fallback (only tests/, __graft_entry__.smoke() and bench.py's CPU legs use the oracle)."""
+    pkg = os.path.join(ROOT, "strutopy_b200")
+    for dirpath, _, files in os.walk(pkg):
+        if "build" in dirpath:
+            continue
+        for fn in files:
+            if not fn.endswith((".py", ".cu", ".cuh", ".h", "Makefile")):
+                continue
+            text = open(os.path.join(dirpath, fn)).read()
+            for line in text.splitlines():
+                code = line.split("#")[0].split("//")[0]
+                assert not re.search(r"\b(import|from)\s+oracle\b", code), f"{fn}: {line.strip()}"
+                assert "libstm_oracle" not in code and "oracle/_ref" not in code, f"{fn}: {line.strip()}"
+    # importing the package pulls in nothing of the oracle
+    out = subprocess.run([sys.executable, "-c", "import sys; sys.path.insert(0, %r); import strutopy_b200, "
+                          "strutopy_b200.spectral, strutopy_b200.generate_docs, strutopy_b200.heldout; "
+                          "print(sorted(m for m in sys.modules if m.split('.')[0] == 'oracle'))" % ROOT],
+                         capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0 and out.stdout.strip() == "[]", out.stdout + out.stderr
