@@ -117,3 +117,19 @@ def test_corpus_creation_mirrors_reference_tests():
     m = STM(corpus.csr, corpus.dictionary, False, K, corpus.metadata, False, 2, 0, 1e-5, init_type="random", model_type="STM")
     m.expectation_maximization(saving=False)
     assert np.all(np.isfinite(m.last_bounds))
+
+
+def test_philox_uniformity():
+    """53-bit uniforms from the oracle's Philox stream: mean / variance / serial correlation of 200k draws."""
+    n = 200000
+    t = np.arange(n, dtype=np.uint64)
+    r0, r1, r2, r3 = cn.philox4x32_10(t & np.uint64(0xFFFFFFFF), np.full(n, 7, np.uint64), np.zeros(n, np.uint64),
+                                      np.zeros(n, np.uint64), 12345, 0)
+    for u in (cn._u53(r0, r1), cn._u53(r2, r3)):
+        assert 0.0 <= u.min() and u.max() < 1.0
+        assert abs(u.mean() - 0.5) < 4 * np.sqrt(1 / 12 / n)
+        assert abs(u.var() - 1 / 12) < 1e-3
+        assert abs(np.corrcoef(u[:-1], u[1:])[0, 1]) < 0.01
+        hist = np.bincount((u * 64).astype(int), minlength=64)
+        chi2 = ((hist - n / 64) ** 2 / (n / 64)).sum()
+        assert chi2 < 120          # 63 degrees of freedom: P(chi2 > 120) ~ 1e-5

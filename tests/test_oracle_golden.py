@@ -151,3 +151,26 @@ def test_mstep_regularised_modes_vs_live_reference(design):
     assert 0 < np.count_nonzero(ref) < ref.size          # the fixture exercises both sides of the threshold
     np.testing.assert_array_equal(coef == 0, ref == 0)
     np.testing.assert_allclose(coef, ref, rtol=1e-10, atol=1e-12)
+
+
+def test_lasso_from_moments_satisfies_the_kkt_conditions():
+    """Independent of sklearn: the coordinate-descent restatement stops at a point whose duality gap is below
+    tol * y'y, i.e. close to the Lasso optimum — zero coefficients have |x_j'r| <= alpha N (within the gap), active
+    ones x_j'r = alpha N sign(w_j)."""
+    rng = np.random.default_rng(3)
+    for p, T, N in ((2, 5, 400), (5, 3, 300), (1, 4, 150)):
+        X = rng.integers(0, 2, size=(N, p)).astype(float)
+        Gam = rng.choice([-9.0, -5.0, 0.0, 0.5, 6.0], size=(T, p))
+        Y = X @ Gam.T + rng.normal(0, 0.7, size=(N, T))
+        xc, yc = X - X.mean(0), Y - Y.mean(0)
+        G, B, yy = xc.T @ xc, xc.T @ yc, (yc * yc).sum(0)
+        coef = stm_numpy.lasso_from_moments(G, B, yy, N)
+        import sklearn.linear_model
+        ref = sklearn.linear_model.Lasso(alpha=1, fit_intercept=True).fit(X, Y).coef_.reshape(T, p)
+        np.testing.assert_allclose(coef, ref, rtol=1e-9, atol=1e-11)
+        for t in range(T):
+            corr = B[:, t] - G @ coef[t]                      # x_j' residual
+            slack = 2e-2 * N                                   # the 1e-4 duality-gap stop leaves this much
+            assert np.all(np.abs(corr[coef[t] == 0]) <= N + slack)
+            act = coef[t] != 0
+            np.testing.assert_allclose(corr[act], N * np.sign(coef[t][act]), atol=slack)
