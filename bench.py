@@ -282,8 +282,12 @@ def ours(args):
 
     # ---- e2e: the reference-facing host call (stm_estep_host) with pinned fp64 host buffers ----------
     K1 = K - 1
-    from oracle import stm_numpy  # checker / CPU baseline only (never on the measured path)
-    siginv, ent = stm_numpy.prologue(snap["sigma"])
+    # the host-side prologue a reference-side caller keeps (stm.py:499-501): plain NumPy here —
+    # oracle/ is only imported by the cpu_baseline / parity leg below and by the reference arm
+    chol = np.linalg.cholesky(snap["sigma"])
+    ent = float(np.sum(np.log(np.diag(chol))))
+    inv_chol = np.linalg.inv(chol)
+    siginv = inv_chol.T * inv_chol
     pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory()  # noqa: E731
     hb = dict(beta=pin(snap["beta"]), mu=pin(snap["mu"]), siginv=pin(siginv), eta=pin(snap["eta0"]),
               theta=torch.empty((D, K), dtype=torch.float64).pin_memory(),
