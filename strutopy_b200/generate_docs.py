@@ -24,6 +24,7 @@ import logging
 import numpy as np
 
 from . import _lib
+from .heldout import cut_in_half as _cut_in_half, split_corpus as _split_docs
 
 logger = logging.getLogger(__name__)
 
@@ -76,106 +77,109 @@ def renumber_by_first_appearance(word_id):
     return new_of_old[np.searchsorted(uniq, word_id)].astype(np.int32), uniq[order]
 
 
+def _alpha_vector(alpha, K):
+    """Dirichlet concentration of the LDA data-generating process (generate_docs.py:139-151)."""
+    if isinstance(alpha, np.ndarray):
+        return alpha
+    ranks = np.arange(1, K + 1)
+    named = {"symmetric": np.full(K, 1.0 / K), "asymmetric": 1.0 / (ranks + np.sqrt(ranks))}
+    return named[alpha] if isinstance(alpha, str) and alpha in named else np.repeat(alpha, K)
+
+
+def _softmax_rows(eta):
+    """theta = softmax([eta, 0]) row by row, max-shifted like the reference's stable_softmax (generate_docs.py:20-24, 268-271)."""
+    full = np.concatenate([eta, np.zeros((eta.shape[0], 1))], axis=1)
+    e = np.exp(full - full.max(axis=1, keepdims=True))
+    return e / e.sum(axis=1, keepdims=True)
+
+
 class CorpusCreation:
-    """generate_docs.py:28-137.  Extra keywords: `device`, `seed` (of the device sampler)."""
+    """generate_docs.py:28-137.  Extra keywords: `device`, `seed` (of the device sampler).
+
+    The constructor consumes the two random streams in the reference's order — `default_rng(12345)` for beta,
+    the metadata and the LDA thetas, NumPy's legacy global stream for gamma and eta (generate_docs.py:129-137) — so a
+    caller that seeds `np.random` as the reference's scripts do (04_create_synthetic_corpora.py:45-47) gets the
+    reference's beta, gamma, metadata and (up to 50 000 documents) eta."""
 
     def __init__(self, n_topics, n_docs, n_words, V, level, treatment=False, alpha="symmetric", dgp="STM",
                  metadata=None, alpha_treatment=None, beta=None, theta=None, gamma=None, device=0, seed=12345):
-        self.K = n_topics
-        self.n_docs = n_docs
-        self.n_words = n_words
-        self.V = V
-        self.dgp = dgp
-        self.level = level
-        self.treatment = treatment
-        self.device = device
-        self.seed = seed
-        self.rng = np.random.default_rng(12345)   # generate_docs.py:129
+        self.K, self.n_docs, self.n_words, self.V = n_topics, n_docs, n_words, V
+        self.dgp, self.level, self.treatment = dgp, level, treatment
+        self.device, self.seed = device, seed
+        self.csr = None
+        self._documents = None
+        self.rng = np.random.default_rng(12345)
         self.init_alpha(alpha, alpha_treatment, theta)
         self.word_topic_dist(beta)
         self.init_gamma(gamma)
         self.set_metadata(metadata)
         self.init_eta()
         self.init_theta(theta)
-        self.csr = None
-        self._documents = None
 
-    # ---- parameter draws: the reference's own NumPy calls (generate_docs.py:139-271) ----------------
+    # ---- parameter draws (generate_docs.py:139-271): same distributions, same order of RNG calls -------
     def init_alpha(self, alpha, alpha_treatment, theta):
-        if type(alpha) == np.ndarray:
-            self.alpha = alpha
-        elif alpha == "symmetric":
-            self.alpha = np.repeat((1 / self.K), self.K)
-        elif alpha == "asymmetric":
-            self.alpha = 1 / (np.array(range(1, self.K + 1)) + np.sqrt(np.array(range(1, self.K + 1))))
-        else:
-            self.alpha = np.repeat(alpha, self.K)
-        if not np.any(self.alpha):
-            assert theta is not None, "Either alpha or theta needs to be specified for generating documents."
-        if self.treatment == True:  # noqa: E712
+        self.alpha = _alpha_vector(alpha, self.K)
+        if not np.any(self.alpha) and theta is None:
+            raise AssertionError("Either alpha or theta needs to be specified for generating documents.")
+        if self.treatment:
             self.init_treatment(alpha_treatment)
 
     def init_treatment(self, alpha_treatment):
-        assert alpha_treatment is not None, "If treatment == True, the effect needs to be specified by alpha_treatment"
-        if type(alpha_treatment) == np.ndarray:
+        if alpha_treatment is None:
+            raise AssertionError("If treatment == True, the effect needs to be specified by alpha_treatment")
+        if isinstance(alpha_treatment, np.ndarray):
             self.alpha_treatment = alpha_treatment
-        elif alpha_treatment == "auto-linear":
-            self.alpha_treatment = np.flip(self.alpha)
-        elif alpha_treatment == "auto-nonlinear":
-            self.alpha_treatment = np.exp(self.alpha)
+        else:
+            auto = {"auto-linear": lambda a: np.flip(a), "auto-nonlinear": lambda a: np.exp(a)}
+            if alpha_treatment in auto:
+                self.alpha_treatment = auto[alpha_treatment](self.alpha)
 
     def word_topic_dist(self, beta):
-        if beta is None:
-            self.beta = self.rng.dirichlet(size=self.K, alpha=np.repeat(0.05, self.V))
-        else:
-            self.beta = np.array(beta)
+        # K draws from Dirichlet(0.05 * 1_V) unless the caller brings a topic-word matrix (generate_docs.py:172-184)
+        self.beta = np.asarray(beta) if beta is not None else self.rng.dirichlet(np.full(self.V, 0.05), size=self.K)
 
     def init_gamma(self, gamma, mean=None):
-        if gamma is None:
-            if mean is None:
-                mean = np.random.standard_normal(self.level)
-            sigma_prior = np.diag(np.full(self.level, 0.001))
-            mean = np.random.multivariate_normal(mean, sigma_prior)
-            sigma = np.diag(np.full(self.level, 0.001))
-            self.gamma = np.random.multivariate_normal(mean, sigma, self.K - 1)
-        else:
+        # prevalence coefficients (K-1) x level around a N(., 0.001 I) draw of their mean (generate_docs.py:186-203)
+        if gamma is not None:
             self.gamma = gamma
+            return
+        small = 0.001 * np.eye(self.level)
+        centre = np.random.standard_normal(self.level) if mean is None else mean
+        centre = np.random.multivariate_normal(centre, small)
+        self.gamma = np.random.multivariate_normal(centre, small, self.K - 1)
 
     def set_metadata(self, metadata, metadata_levels=[0, 1]):
-        if metadata is None:
-            self.metadata = self.rng.choice(metadata_levels, size=(int(self.n_docs), self.level), replace=True, p=None)
-        else:
+        if metadata is not None:
             assert metadata.shape == (self.n_docs, self.level), "Unexpected metadata shape provided."
             self.metadata = metadata
+        else:   # iid levels per document and covariate (generate_docs.py:205-219)
+            self.metadata = self.rng.choice(metadata_levels, size=(int(self.n_docs), self.level), replace=True, p=None)
 
     def init_eta(self):
-        mu = self.metadata @ self.gamma.T
-        if self.n_docs <= 50000:
-            sigma = np.diag(np.full(self.K - 1, 0.001))
-            self.eta = np.array([np.random.multivariate_normal(mu[d], sigma) for d in range(self.n_docs)])
+        # eta_d ~ N(x_d gamma', 0.001 I) (generate_docs.py:221-228); beyond 50k documents in one vectorised draw
+        centre = self.metadata @ self.gamma.T
+        if self.n_docs > 50000:
+            self.eta = centre + np.sqrt(0.001) * np.random.standard_normal(centre.shape)
         else:
-            self.eta = mu + np.sqrt(0.001) * np.random.standard_normal((self.n_docs, self.K - 1))
+            cov = 0.001 * np.eye(self.K - 1)
+            self.eta = np.stack([np.random.multivariate_normal(row, cov) for row in centre])
 
     def init_theta(self, theta):
-        if self.dgp == "LDA":
-            if theta is None:
-                if self.treatment == False:  # noqa: E712
-                    self.theta = self.rng.dirichlet(alpha=self.alpha, size=self.n_docs)
-                else:
-                    self.theta = self.rng.dirichlet(alpha=self.alpha, size=int(self.n_docs / 2))
-                    self.theta_treatment = self.rng.dirichlet(alpha=self.alpha_treatment, size=int(self.n_docs / 2))
-            else:
-                self.theta = np.array(theta)
-        elif self.dgp == "STM":
+        if self.dgp == "STM":
             self.map_eta(eta=self.eta)
+        elif self.dgp == "LDA" and theta is None:
+            half = int(self.n_docs / 2)
+            if self.treatment:
+                self.theta = self.rng.dirichlet(self.alpha, size=half)
+                self.theta_treatment = self.rng.dirichlet(self.alpha_treatment, size=half)
+            else:
+                self.theta = self.rng.dirichlet(self.alpha, size=self.n_docs)
         else:
             self.theta = np.array(theta)
             assert self.theta.ndim == 2, "theta needs to be a 2D numpy array"
 
     def map_eta(self, eta):
-        full = np.concatenate([eta, np.zeros((eta.shape[0], 1))], axis=1)
-        e = np.exp(full - full.max(axis=1, keepdims=True))
-        self.theta = e / e.sum(axis=1, keepdims=True)
+        self.theta = _softmax_rows(np.asarray(eta))
 
     # ---- sampling: on the device (generate_docs.py:273-316) -----------------------------------------
     def generate_documents(self, remove_terms=True, dictionary=True, display_props=False):
@@ -231,24 +235,16 @@ class CorpusCreation:
         self.dictionary = {i: str(i) for i in range(int(ids.max()) + 1 if ids.size else 0)}
 
     def split_corpus(self, validation_set=False, document_completion=True, proportion=0.8):
-        """generate_docs.py:381-399"""
-        docs = self.documents
-        test_split_idx = int(proportion * len(docs))
-        self.train_docs = docs[:test_split_idx]
-        if validation_set:
-            validate_split_idx = int((proportion + (1 - proportion) / 2) * len(docs))
-            self.test_docs = docs[test_split_idx:validate_split_idx]
-            self.validate_docs = docs[validate_split_idx:]
-        else:
-            self.test_docs = docs[test_split_idx:]
+        """generate_docs.py:381-399 (same split as heldout.split_corpus, results stored as attributes)"""
+        train, half1, half2, validate = _split_docs(self.documents, validation_set, document_completion, proportion)
+        self.train_docs = train
+        n_train = len(train)
+        self.test_docs = self.documents[n_train:] if validate is None else self.documents[n_train:len(self.documents) - len(validate)]
+        if validate is not None:
+            self.validate_docs = validate
         if document_completion:
-            self.test_1_docs, self.test_2_docs = self.cut_in_half(self.test_docs)
+            self.test_1_docs, self.test_2_docs = half1, half2
 
     def cut_in_half(self, doc_set):
         """generate_docs.py:401-417"""
-        first_half = np.zeros(len(doc_set), dtype=np.ndarray)
-        second_half = np.zeros(len(doc_set), dtype=np.ndarray)
-        for doc in range(len(doc_set)):
-            first_half[doc] = doc_set[doc][0::2]
-            second_half[doc] = doc_set[doc][1::2]
-        return first_half, second_half
+        return _cut_in_half(doc_set)

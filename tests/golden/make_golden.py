@@ -20,6 +20,8 @@ Fixtures (all inputs are stored next to the reference's outputs so tests need no
                        one-hot-encoded (3-level) designs
   mnreg.npz            STM.mnreg (stm.py:749-853) of the live reference (csr_matrix.A restored by the shim) on the
                        content fixture's beta_ss: kappa and beta AS WRITTEN (every word regressed on column 1)
+  corpus_params.npz    CorpusCreation's parameter draws (beta, gamma, metadata, eta, theta) of the live reference after
+                       np.random.seed(12345), STM and LDA(+treatment) data-generating processes
   spectral.npz         spectral_init (stm.py:30-84) of the live reference, `solve_qp` shimmed by exact NNLS
                        (tools/ref_shims.py): two synthetic corpora (vocabulary truncated by maxV / not
                        truncated) and the shipped wiki corpus at K=20 (anchors + every 8th kept column)
@@ -301,6 +303,20 @@ def mnreg():
     save("mnreg.npz", out)
 
 
+def corpus_params():
+    out = {}
+    cfgs = dict(stm=dict(dgp="STM", level=2), lda=dict(dgp="LDA", level=1),
+                ldat=dict(dgp="LDA", level=1, treatment=True, alpha_treatment="auto-linear", alpha="asymmetric"))
+    for tag, kw in cfgs.items():
+        np.random.seed(12345)
+        c = gd_mod.CorpusCreation(n_topics=5, n_docs=40, n_words=30, V=60, **kw)
+        for k in ("alpha", "beta", "gamma", "metadata", "eta", "theta"):
+            out[f"{tag}_{k}"] = np.asarray(getattr(c, k))
+        if kw.get("treatment"):
+            out[f"{tag}_theta_treatment"] = np.asarray(c.theta_treatment)
+    save("corpus_params.npz", out)
+
+
 def spectral():
     """spectral_init of the live reference.  Case t: V=900 > maxV=500 (the `keep` cut is exercised);
     case f: every word kept; case w: the shipped wiki corpus, K=20, maxV=5000 as STM.init_beta calls it."""
@@ -356,6 +372,7 @@ ALL = dict(
     spectral=spectral,
     mstep_modes=mstep_modes,
     mnreg=mnreg,
+    corpus_params=corpus_params,
 )
 
 if __name__ == "__main__":

@@ -133,3 +133,22 @@ def test_philox_uniformity():
         hist = np.bincount((u * 64).astype(int), minlength=64)
         chi2 = ((hist - n / 64) ** 2 / (n / 64)).sum()
         assert chi2 < 120          # 63 degrees of freedom: P(chi2 > 120) ~ 1e-5
+
+
+def test_corpus_creation_parameter_draws_equal_the_live_reference():
+    """The constructor of the CorpusCreation mirror runs on the host: with np.random seeded as the reference's scripts
+    seed it (04_create_synthetic_corpora.py:45-47) it reproduces the reference's alpha, beta, gamma, metadata, eta and
+    theta bit for bit (fixture from the live reference, generate_docs.py:99-271)."""
+    from conftest import load_golden
+    from strutopy_b200.generate_docs import CorpusCreation
+    g = load_golden("corpus_params.npz")
+    cfgs = dict(stm=dict(dgp="STM", level=2), lda=dict(dgp="LDA", level=1),
+                ldat=dict(dgp="LDA", level=1, treatment=True, alpha_treatment="auto-linear", alpha="asymmetric"))
+    for tag, kw in cfgs.items():
+        np.random.seed(12345)
+        c = CorpusCreation(n_topics=5, n_docs=40, n_words=30, V=60, **kw)
+        for k in ("alpha", "beta", "gamma", "metadata", "eta"):
+            np.testing.assert_array_equal(np.asarray(getattr(c, k)), g[f"{tag}_{k}"], err_msg=f"{tag} {k}")
+        np.testing.assert_allclose(c.theta, g[f"{tag}_theta"], rtol=0, atol=1e-16)
+        if kw.get("treatment"):
+            np.testing.assert_array_equal(c.theta_treatment, g[f"{tag}_theta_treatment"])
