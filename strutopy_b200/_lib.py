@@ -6,8 +6,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-# STM_B200_LIB overrides the library path (development A/B builds only)
-LIB_PATH = os.environ.get("STM_B200_LIB") or os.path.join(_HERE, "libstm_b200.so")
+LIB_PATH = os.path.join(_HERE, "libstm_b200.so")
 
 STM_OK = 0
 STM_ERR_INVALID, STM_ERR_CUDA, STM_ERR_NOT_PD, STM_ERR_UNSUPPORTED, STM_ERR_NO_CORPUS = -1, -2, -3, -4, -5
@@ -15,12 +14,15 @@ MODEL_STM, MODEL_CTM, MODEL_STM_RIDGE, MODEL_STM_LASSO = 0, 1, 2, 3
 
 EXPORTS = [
     "stm_create", "stm_destroy", "stm_last_error", "stm_beta_stride", "stm_launch_count", "stm_estep_kernel_ms",
+    "stm_tune",
     "stm_set_corpus", "stm_stats_layout", "stm_prologue", "stm_estep", "stm_moments", "stm_mstep",
     "stm_beta_to_wordmajor", "stm_wordmajor_to_kv", "stm_estep_host", "stm_heldout", "stm_heldout_host",
     "stm_spectral_gram", "stm_spectral_finish", "stm_sample_corpus", "stm_update_kappa",
 ]
 
 _lib = None
+# launch-configuration overrides applied to every new Context (tools/ A/B runs set this; empty = library defaults)
+DEFAULT_TUNE = {}
 
 
 class StmError(RuntimeError):
@@ -49,6 +51,7 @@ def load():
     L.stm_launch_count.argtypes = [vp]
     L.stm_launch_count.restype = i64
     L.stm_estep_kernel_ms.argtypes = [vp, C.POINTER(C.c_double)]
+    L.stm_tune.argtypes = [vp, C.c_char_p, i32]
     L.stm_heldout.argtypes = [vp, i64, vp, vp, vp, vp, vp, vp, vp, vp]
     L.stm_heldout_host.argtypes = [vp, i64, vp, vp, vp, vp, vp, vp, C.POINTER(C.c_double)]
     L.stm_spectral_gram.argtypes = [vp, i32, vp, vp, vp]
@@ -88,13 +91,15 @@ def hp(a):
 class Context:
     """Owns one stm_ctx (one GPU)."""
 
-    def __init__(self, K, V, A=1, device=0):
+    def __init__(self, K, V, A=1, device=0, tune=None):
         L = load()
         self._h = C.c_void_p()
         rc = L.stm_create(int(device), int(K), int(V), int(A), C.byref(self._h))
         if rc != STM_OK:
             msg = L.stm_last_error(None)
             raise StmError(rc, msg.decode() if msg else "")
+        for key, value in (tune or DEFAULT_TUNE).items():
+            check(self._h, L.stm_tune(self._h, key.encode(), int(value)))
         self.K, self.V, self.A, self.device = int(K), int(V), int(A), int(device)
         self.K1 = self.K - 1
         self.TS = L.stm_beta_stride(self.K)

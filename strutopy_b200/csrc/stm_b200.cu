@@ -3,6 +3,7 @@
 // include/stm_b200.h.  Reference behaviour cited per function (stm.py = /root/reference/src/modules/stm.py).
 #include "../../include/stm_b200.h"
 #include "estep_kernel.cuh"
+#include "bfgs_slots.cuh"
 
 #include <cublas_v2.h>
 #include <cusolverDn.h>
@@ -30,6 +31,9 @@ struct LengthClass {
     int post_warps = 0, post_smem_per_warp = 0, post_grid = 0;
     int post_groups = 0;   // > 0: group version of kernel B, this many documents per CTA
     int post_gw = 3;       //      warps per document there
+    // kernel A, slots version (bfgs_slots.cuh): warps per CTA, TMEM slots per warp, shared-memory tiles per CTA,
+    // bytes of a slot's small block, TMEM columns per slot, CTAs; s_warps == 0: not available for this class
+    int s_warps = 0, s_tm_slots = 0, s_tiles = 0, s_small = 0, s_tm_cols = 0, s_grid = 0;
 };
 
 }  // namespace
@@ -72,6 +76,8 @@ struct stm_ctx {
     cublasHandle_t cublas = nullptr;
     cusolverDnHandle_t cusolver = nullptr;
     int64_t launches = 0;
+    // stm_tune: kernel A version (1: document slots, 0: one warp per document) and its warps per CTA
+    int tune_bfgs_slots = 1, tune_bfgs_warps = 8;
     cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};   // E-step phases: before kernel A, between, after kernel B
     cudaStream_t copy_stream = nullptr;                // host API: eta goes home while kernel B runs
     std::string err;
@@ -163,6 +169,10 @@ cudaError_t stm_launch_bfgs_kpl1(const stm::EstepParams&, int, int, int, size_t,
 cudaError_t stm_launch_bfgs_kpl2(const stm::EstepParams&, int, int, int, size_t, cudaStream_t);
 cudaError_t stm_launch_bfgs_kpl3(const stm::EstepParams&, int, int, int, size_t, cudaStream_t);
 cudaError_t stm_launch_bfgs_kpl4(const stm::EstepParams&, int, int, int, size_t, cudaStream_t);
+cudaError_t stm_launch_bfgs_slots_kpl1(const stm::EstepParams&, int, int, int, size_t, cudaStream_t);
+cudaError_t stm_launch_bfgs_slots_kpl2(const stm::EstepParams&, int, int, int, size_t, cudaStream_t);
+cudaError_t stm_launch_bfgs_slots_kpl3(const stm::EstepParams&, int, int, int, size_t, cudaStream_t);
+cudaError_t stm_launch_bfgs_slots_kpl4(const stm::EstepParams&, int, int, int, size_t, cudaStream_t);
 cudaError_t stm_launch_post_kpl1(const stm::EstepParams&, int, int, size_t, cudaStream_t);
 cudaError_t stm_launch_post_kpl2(const stm::EstepParams&, int, int, size_t, cudaStream_t);
 cudaError_t stm_launch_post_kpl3(const stm::EstepParams&, int, int, size_t, cudaStream_t);
@@ -182,6 +192,43 @@ cudaError_t launch_bfgs(int KPL, const stm::EstepParams& P, int J, int grid, int
         default: return stm_launch_bfgs_kpl4(P, J, grid, block, smem, st);
     }
 }
+cudaError_t launch_bfgs_slots(int KPL, const stm::EstepParams& P, int J, int grid, int block, size_t smem,
+                              cudaStream_t st) {
+    switch (KPL) {
+        case 1: return stm_launch_bfgs_slots_kpl1(P, J, grid, block, smem, st);
+        case 2: return stm_launch_bfgs_slots_kpl2(P, J, grid, block, smem, st);
+        case 3: return stm_launch_bfgs_slots_kpl3(P, J, grid, block, smem, st);
+        default: return stm_launch_bfgs_slots_kpl4(P, J, grid, block, smem, st);
+    }
+}
+// Slots version of kernel A (bfgs_slots.cuh): how many warps, TMEM slots per warp and shared-memory tiles fit.
+// A warp can only address its own 32-lane quarter of tensor memory; a quarter holds 2 documents of <= 256
+// columns or 1 of <= 512, so <= 4 warps take 2 TMEM slots each and 5..8 warps one.
+void config_slots(const stm_ctx* ctx, LengthClass& lc) {
+    const int K = ctx->K, TS = ctx->TS;
+    const int wslots = (lc.n_cap + 31) / 32, CS = (K + 1) & ~1;
+    int per_quarter = 0;
+    if (lc.n_cap <= 32 * lc.J) per_quarter = (wslots * CS <= 256) ? 2 : ((wslots * CS <= 512) ? 1 : 0);
+    int W = std::max(1, std::min(ctx->tune_bfgs_warps, STM_SLOTS_MAX_THREADS / 32));
+    int TW = 0;
+    if (per_quarter == 2) TW = (W <= 4) ? 2 : 1;
+    else if (per_quarter == 1) { TW = 1; W = std::min(W, 4); }
+    const size_t small_b = stm::slots_small_bytes(K, TS, lc.n_cap);
+    const size_t tile_b = stm::slots_tile_bytes(lc.n_cap, TS);
+    const long long avail = (long long)ctx->max_smem - 256 - (long long)W * TW * (long long)small_b;
+    int NS = avail > 0 ? (int)(avail / (long long)(small_b + tile_b)) : 0;
+    NS = std::min(NS, W * (stm::SLOT_GMAX - TW));
+    if (avail < 0) { lc.s_warps = 0; return; }
+    if (TW == 0) {
+        if (NS < 1) { lc.s_warps = 0; return; }
+        W = std::min(W, NS);
+    }
+    lc.s_warps = W; lc.s_tm_slots = TW; lc.s_tiles = NS; lc.s_small = (int)small_b;
+    lc.s_tm_cols = (per_quarter == 2) ? 256 : 512;
+    const int per_cta = W * TW + NS;
+    lc.s_grid = std::min(ctx->sm_count, (lc.n_docs + per_cta - 1) / per_cta);
+}
+
 cudaError_t launch_post(int KPL, const stm::EstepParams& P, int grid, int block, size_t smem, cudaStream_t st) {
     switch (KPL) {
         case 1: return stm_launch_post_kpl1(P, grid, block, smem, st);
@@ -624,6 +671,21 @@ int stm_estep_kernel_ms(stm_ctx* ctx, double* ms2) {
     return STM_OK;
 }
 
+// Tuning interface (explicit; the library reads no environment variables).  Takes effect at the next
+// stm_set_corpus.  Keys: "bfgs_slots" (1: document-slot version of kernel A, 0: one warp per document),
+// "bfgs_warps" (warps per CTA of the slot version, 1..8).
+int stm_tune(stm_ctx* ctx, const char* key, int value) {
+    if (!ctx || !key) return STM_ERR_INVALID;
+    const std::string k(key);
+    if (k == "bfgs_slots") { ctx->tune_bfgs_slots = value ? 1 : 0; return STM_OK; }
+    if (k == "bfgs_warps") {
+        if (value < 1 || value > STM_SLOTS_MAX_THREADS / 32) return fail(ctx, STM_ERR_INVALID, "bfgs_warps must be in 1..8");
+        ctx->tune_bfgs_warps = value;
+        return STM_OK;
+    }
+    return fail(ctx, STM_ERR_INVALID, "stm_tune: unknown key " + k);
+}
+
 int stm_create(int device, int K, int V, int A, stm_ctx** out) {
     stm_ctx* ctx = nullptr;
     if (!out) return fail(ctx, STM_ERR_INVALID, "out is NULL");
@@ -739,10 +801,6 @@ int stm_set_corpus(stm_ctx* ctx, int64_t D, const int64_t* doc_ptr, const int32_
                 if (slots * CS <= 256) { lc.tm_warps = 8; lc.tm_cols = 256; }
                 else if (slots * CS <= 512) { lc.tm_warps = 4; lc.tm_cols = 512; }
             }
-            if (const char* e = getenv("STM_TM_WARPS")) {  // development knob
-                const int c = atoi(e);
-                if (c == 0 || (c == 4 && lc.tm_warps >= 4)) { lc.tm_warps = c; lc.tm_cols = c ? 512 : 0; }
-            }
             const int max_w = STM_BFGS_MAX_THREADS / 32;
             const int avail = ctx->max_smem - 128 - lc.tm_warps * lc.smem_small;   // 128: static shared (TMEM base)
             int sw = avail > 0 ? avail / (lc.smem_small + lc.smem_per_warp) : 0;
@@ -751,17 +809,13 @@ int stm_set_corpus(stm_ctx* ctx, int64_t D, const int64_t* doc_ptr, const int32_
         }
         lc.post_smem_per_warp = (int)post_smem_per_warp(lc.n_cap, ctx->TS, ctx->K1, ctx->KPL);
         lc.post_warps = std::min(8, ctx->max_smem / lc.post_smem_per_warp);
-        if (const char* cap = getenv("STM_MAX_WARPS")) {  // development knob (occupancy experiments)
-            const int c = atoi(cap);
-            if (c >= 1) { lc.warps = std::min(lc.warps, c); lc.post_warps = std::min(lc.post_warps, c); }
-        }
         if (lc.warps < 1 || lc.post_warps < 1)
             return fail(ctx, STM_ERR_UNSUPPORTED,
                         "a document's beta tile (" + std::to_string(lc.post_smem_per_warp) +
                             " bytes) does not fit in shared memory");
         lc.grid = std::min(ctx->sm_count, (lc.n_docs + lc.warps - 1) / lc.warps);
         lc.post_grid = std::min(ctx->sm_count, (lc.n_docs + lc.post_warps - 1) / lc.post_warps);
-        if (!getenv("STM_NO_POST_GROUPS")) {
+        {
             const int gw = post_group_warps(ctx->K1, ctx->KPL);
             const int per_group = (int)post_group_smem(lc.n_cap, ctx->TS, ctx->K1, ctx->KPL, gw);
             const int g = std::min(stm::post_group_max_threads(gw) / (32 * gw), ctx->max_smem / per_group);
@@ -776,6 +830,10 @@ int stm_set_corpus(stm_ctx* ctx, int64_t D, const int64_t* doc_ptr, const int32_
             }
         }
         max_warps = std::max(max_warps, std::max(lc.grid * lc.warps, lc.post_grid * lc.post_warps));
+        if (ctx->tune_bfgs_slots) {
+            config_slots(ctx, lc);
+            max_warps = std::max(max_warps, lc.s_grid * lc.s_warps * stm::SLOT_GMAX);
+        }
         CU(cudaMalloc(&lc.d_docs, sizeof(int) * lc.n_docs));
         CU(cudaMemcpy(lc.d_docs, members[ci].data(), sizeof(int) * lc.n_docs, cudaMemcpyHostToDevice));
         max_warps = std::max(max_warps, lc.grid * lc.warps);
@@ -809,7 +867,7 @@ int stm_set_corpus(stm_ctx* ctx, int64_t D, const int64_t* doc_ptr, const int32_
     return STM_OK;
 }
 
-#if STM_DBG_TIMING
+#if STM_DBG_TIMING || STM_SLOTS_TIMING
 // variant builds only (not part of include/stm_b200.h): read and reset the per-phase cycle counters
 int stm_dbg_cycles(stm_ctx* ctx, unsigned long long* out8) {
     cudaMemcpy(out8, ctx->d_dbg, sizeof(unsigned long long) * 16, cudaMemcpyDeviceToHost);
@@ -855,7 +913,6 @@ int stm_estep(stm_ctx* ctx, const float* beta_t_dev, const double* mu_dev, const
     CU(cudaMemsetAsync(stats_dev + off[0], 0, sizeof(double) * (size_t)ctx->A * ctx->V * ctx->TS, st));
     CU(cudaMemsetAsync(ctx->d_sigma_rep, 0, sizeof(double) * ctx->n_rep * K1 * K1, st));
     CU(cudaMemsetAsync(ctx->d_queues, 0, sizeof(unsigned int) * 32, st));
-    static const int dev_skip = getenv("STM_DEV_SKIP") ? atoi(getenv("STM_DEV_SKIP")) : 0;  // 1: no kernel A, 2: no kernel B (timing only)
     // kernel A (BFGS) for every length class, then kernel B (post-optimisation) for every length class;
     // three events bracket the two phases (stm_estep_kernel_ms)
     CU(cudaEventRecord(ctx->ev[0], st));
@@ -874,12 +931,20 @@ int stm_estep(stm_ctx* ctx, const float* beta_t_dev, const double* mu_dev, const
             P.scratch = ctx->d_scratch; P.scratch_stride = ctx->scratch_stride;
             P.n_cap = lc.n_cap; P.smem_per_warp = lc.smem_per_warp;
             P.smem_small = lc.smem_small; P.tm_warps = lc.tm_warps; P.tm_cols = lc.tm_cols;
+            P.tm_slots = 0; P.smem_tiles = 0;
             P.dbg_cycles = ctx->d_dbg;
             if (phase == 0) {
-                if (dev_skip != 1)
+                if (lc.s_warps > 0) {
+                    P.smem_small = lc.s_small; P.tm_slots = lc.s_tm_slots; P.smem_tiles = lc.s_tiles;
+                    P.tm_cols = lc.s_tm_cols;
+                    const size_t smem = (size_t)(lc.s_warps * lc.s_tm_slots + lc.s_tiles) * lc.s_small +
+                                        (size_t)lc.s_tiles * stm::slots_tile_bytes(lc.n_cap, ctx->TS);
+                    CU(launch_bfgs_slots(ctx->KPL, P, lc.J, lc.s_grid, lc.s_warps * 32, smem, st));
+                } else {
                     CU(launch_bfgs(ctx->KPL, P, lc.J, lc.grid, lc.warps * 32,
                                    (size_t)lc.smem_small * lc.warps + (size_t)lc.smem_per_warp * (lc.warps - lc.tm_warps), st));
-            } else if (dev_skip != 2) {
+                }
+            } else {
                 P.smem_per_warp = lc.post_smem_per_warp;
                 if (lc.post_groups > 0) {
                     const size_t smem = (size_t)lc.post_smem_per_warp * lc.post_groups;

@@ -12,6 +12,10 @@ Fixtures (all inputs are stored next to the reference's outputs so tests need no
   estep_K50.npz        D=64  V~1900 K=50, EM iterations 0 and 1 (PD-repair branch hot in iteration 0)
   estep_content.npz    A=2 aspects (content=True, kappa_interactions=True), K=8, one E-step + M-step
   em_c1.npz            config 1 (D=200 V=500 K=5, 1 covariate) full EM to convergence: ELBO trace + final state
+  em_c2.npz            config 2 (D=10k V=5k K=20, 2 covariates): the reference-generated corpus + the live reference's
+                       20-iteration ELBO trace on its first 300 documents
+  em_k50.npz           K=50, D=2000 corpus, the live reference's spectral beta0 (fp32) + its 25-iteration ELBO trace on
+                       the first 200 documents with that beta0 injected
   em_toy_ctm.npz       the reference's own tests/test_integration.py toy pipeline (K=3, CTM, 2 iterations)
   wiki_corpus.npz      the reference's shipped wiki BoW corpus + X + its shipped iteration-0 ELBOs (K=50, 70)
   mstep_modes.npz      update_mu / update_sigma of the live reference in its regularised modes (stm.py:678-688:
@@ -360,6 +364,71 @@ def spectral():
     save("spectral.npz", out)
 
 
+def pack_csr(ptr, ids, cnt):
+    """compact storage of a corpus: lengths uint16, ids uint16, counts uint8 (checked)"""
+    ln = np.diff(ptr)
+    assert ln.max() < 65536 and ids.max() < 65536 and cnt.max() < 256 and np.all(cnt == np.round(cnt))
+    return ln.astype(np.uint16), ids.astype(np.uint16), cnt.astype(np.uint8)
+
+
+def em_c2():
+    """BASELINE.json configs[1]: D=10k, V=5k, K=20, 2 prevalence covariates, 20 EM iterations.  The corpus is drawn
+    by the live reference's CorpusCreation exactly as src/04_create_synthetic_corpora.py does (np.random.seed(12345),
+    150 words per document, remove_terms=False) and stored whole; the live reference itself is run on the first
+    300 documents (a full fit would take ~2 h on one core) — the anchor for the C oracle's and the CUDA path's
+    20-iteration traces; the full-size traces are compared GPU vs C oracle at test time."""
+    K, V, D, CUT = 20, 5000, 10000, 300
+    np.random.seed(12345)
+    corpus = gd_mod.CorpusCreation(n_topics=K, n_docs=D, n_words=150, V=V, level=2, dgp="STM")
+    corpus.generate_documents(remove_terms=False)
+    ptr, ids, cnt = to_csr(corpus.documents)
+    out = {}
+    out["doc_len"], out["word_id"], out["count"] = pack_csr(ptr, ids, cnt)
+    out["X"] = np.array(corpus.metadata, dtype=np.float64)
+    Vd = len(corpus.dictionary)
+    out["K"], out["V"], out["cut"] = np.int64(K), np.int64(Vd), np.int64(CUT)
+    m = make_model(corpus.documents[:CUT], corpus.dictionary, K, np.array(corpus.metadata)[:CUT], 20)
+    out["cut_beta0"] = np.array(m.beta)
+    m.expectation_maximization(saving=False)
+    out["cut_bounds"] = np.array(m.last_bounds)
+    for k in ("gamma", "sigma"):
+        out["cut_final_" + k] = np.array(getattr(m, k))
+    out["cut_final_theta"] = np.array(m.theta)
+    print("em_c2: V", Vd, "nnz", len(ids), "cut iterations", len(m.last_bounds), "final bound", m.last_bounds[-1])
+    save("em_c2.npz", out)
+
+
+def em_k50():
+    """K=50 from a spectral initialisation, 25 EM iterations (BASELINE config 3's regime at a size the oracle runs in
+    seconds): D=2000, V=2000 corpus from tests/conftest.synthetic_corpus; beta0 = the live reference's spectral_init
+    (solve_qp shimmed by exact NNLS) on the whole corpus, rounded to fp32; the live reference's EM trace on the
+    first 200 documents with that beta0 injected is the anchor."""
+    sys.path.insert(0, os.path.join(HERE, ".."))
+    from conftest import synthetic_corpus
+    K, V, D, CUT = 50, 2000, 2000, 200
+    ptr, ids, cnt, X, _ = synthetic_corpus(D, V, K, n_words=150, seed=4242)
+    seen = np.unique(ids)                       # every word must occur (stm.py:152-154) -> compact ids
+    ids = np.searchsorted(seen, ids).astype(np.int32)
+    V = len(seen)
+    docs = [[(int(ids[j]), int(cnt[j])) for j in range(ptr[d], ptr[d + 1])] for d in range(D)]
+    beta0 = stm_mod.spectral_init(docs, K, V, maxV=5000, verbose=False)
+    beta0 = np.asarray(beta0, dtype=np.float32)
+    out = {}
+    out["doc_len"], out["word_id"], out["count"] = pack_csr(ptr, ids, cnt)
+    out["X"] = X
+    out["K"], out["V"], out["cut"] = np.int64(K), np.int64(V), np.int64(CUT)
+    out["beta0"] = beta0
+    dictionary = {i: str(i) for i in range(V)}
+    m = make_model(docs[:CUT], dictionary, K, X[:CUT], 25)
+    m.beta = beta0.astype(np.float64)
+    m.expectation_maximization(saving=False)
+    out["cut_bounds"] = np.array(m.last_bounds)
+    out["cut_final_gamma"] = np.array(m.gamma)
+    out["cut_final_sigma"] = np.array(m.sigma)
+    print("em_k50: V", V, "cut iterations", len(m.last_bounds), "final bound", m.last_bounds[-1])
+    save("em_k50.npz", out)
+
+
 ALL = dict(
     kat_small=kat_small,
     estep_K5=lambda: estep_fixture("estep_K5.npz", 5, 500, 200, 12345, {0, 2}, 3),
@@ -367,6 +436,8 @@ ALL = dict(
     estep_K50=lambda: estep_fixture("estep_K50.npz", 50, 2000, 64, 2, {0, 1}, 2, keep_m_beta=False),
     estep_content=estep_content,
     em_c1=em_c1,
+    em_c2=em_c2,
+    em_k50=em_k50,
     em_toy_ctm=em_toy_ctm,
     wiki_corpus=wiki_corpus,
     spectral=spectral,

@@ -1,5 +1,5 @@
 """A/B timing of the E-step kernel (development tool).  Usage on the GPU box:
-    STM_B200_LIB=path/to/lib.so python tools/gpu_perf.py [--iters 4] [--docs 100000]
+    python tools/gpu_perf.py [--iters 4] [--docs 100000] [--tune bfgs_slots=1,bfgs_warps=6]
 Prints per-EM-iteration E-step kernel time (CUDA events), mean evaluations per document, ELBO."""
 import argparse
 import os
@@ -19,11 +19,21 @@ def main():
     ap.add_argument("--docs", type=int, default=100000)
     ap.add_argument("--K", type=int, default=50)
     ap.add_argument("--V", type=int, default=10000)
-    ap.add_argument("--tag", default=os.environ.get("STM_B200_LIB", "default"))
+    ap.add_argument("--tag", default="default")
     ap.add_argument("--init", default="random", choices=["random", "spectral"])
     ap.add_argument("--heldout", action="store_true", help="also time STM.eval_heldout on the training corpus")
+    ap.add_argument("--tune", default="", help="stm_tune overrides, e.g. bfgs_slots=1,bfgs_warps=6")
+    ap.add_argument("--slots-timing", action="store_true", help="the library is a -DSTM_SLOTS_TIMING=1 build")
+    ap.add_argument("--lib", default="", help="path of an A/B build of the library (make variant)")
     a = ap.parse_args()
     import torch
+    from strutopy_b200 import _lib as lib_
+    if a.lib:
+        lib_.LIB_PATH = os.path.abspath(a.lib)
+        a.tag = a.lib
+    if a.tune:
+        lib_.DEFAULT_TUNE = {kv.split("=")[0]: int(kv.split("=")[1]) for kv in a.tune.split(",")}
+        a.tag = a.tune
     cache = f"/tmp/corpus_{a.docs}_{a.V}_{a.K}.npz"
     if os.path.exists(cache):
         z = np.load(cache)
@@ -55,10 +65,18 @@ def main():
             fn = L_.load().stm_dbg_cycles
             arr = (C.c_ulonglong * 16)()
             fn(m._ctx.handle, arr)
-            tot = sum(arr[:8]) or 1
-            names = ["gather+a_k", "eval", "linesearch", "accept/Hupd", "theta", "colsum+hess", "chol", "bound+inv+nu",
-                     "e:memo+max", "e:exp", "e:contract+lp", "e:log(prod)", "e:reduce", "e:lse+grad", "-", "-"]
-            out.append("      cycles/doc/warp: " + "  ".join(f"{nm} {c/len(d['nfev']):.0f} ({c/tot*100:.0f}%)" for nm, c in zip(names, arr)))
+            if a.slots_timing:
+                rounds, fresh, memo = arr[8] or 1, arr[9] or 1, arr[10]
+                names = ["refill", "evals", "scalar", "accept", "scalar2", "finalize"]
+                tot = sum(arr[:6]) or 1
+                out.append(f"      rounds {rounds}  fresh evals {fresh}  memo hits {memo}  cycles/round: " +
+                           "  ".join(f"{nm} {c/rounds:.0f} ({c/tot*100:.0f}%)" for nm, c in zip(names, arr)) +
+                           f"  | per fresh eval: exp+partials {arr[11]/fresh:.0f}  contraction {arr[12]/fresh:.0f}  log+reduce {arr[13]/fresh:.0f}")
+            else:
+                tot = sum(arr[:8]) or 1
+                names = ["gather+a_k", "eval", "linesearch", "accept/Hupd", "theta", "colsum+hess", "chol", "bound+inv+nu",
+                         "e:memo+max", "e:exp", "e:contract+lp", "e:log(prod)", "e:reduce", "e:lse+grad", "-", "-"]
+                out.append("      cycles/doc/warp: " + "  ".join(f"{nm} {c/len(d['nfev']):.0f} ({c/tot*100:.0f}%)" for nm, c in zip(names, arr)))
         except AttributeError:
             pass
         nf = d['nfev']
