@@ -61,9 +61,8 @@ int64_t stm_launch_count(const stm_ctx* ctx);
  * (theta, phi, Hessian, Cholesky pivots, bound, nu; stm.py:546-590).  Blocks until that call is done. */
 int stm_estep_kernel_ms(stm_ctx* ctx, double* ms2);
 /* tuning of the E-step launch configuration (no reference counterpart; the library reads no environment
- * variables).  Takes effect at the next stm_set_corpus.  Keys: "bfgs_slots" (1, default: the document-slot
- * version of kernel A, several documents per warp; 0: one warp per document), "bfgs_warps" (1..8: warps per
- * CTA of the slot version). */
+ * variables).  Takes effect at the next stm_set_corpus.  Keys: "bfgs_max_warps" (cap on the warps, i.e.
+ * documents in flight, per SM of kernel A; occupancy studies). */
 int stm_tune(stm_ctx* ctx, const char* key, int value);
 
 /* ---- corpus ------------------------------------------------------------------------------------ */

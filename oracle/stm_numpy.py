@@ -208,18 +208,25 @@ def update_beta(beta_ss):
 
 
 def em(doc_ptr, word_id, count, beta0, X, n_iter, model="STM", mode="ols", sigprior=0.0,
-       threshold=1e-5, aspect=None, estep_fn=None):
-    """EM loop (stm.py:855-903) from the reference's initial state (mu=0, eta=0, Sigma=20 I)."""
+       threshold=1e-5, aspect=None, estep_fn=None, round_beta32=False, keep_states=False):
+    """EM loop (stm.py:855-903) from the reference's initial state (mu=0, eta=0, Sigma=20 I).
+    round_beta32: round beta to fp32-representable values after every M-step (what the CUDA path's fp32 beta storage
+    does), so that a trace can be compared step by step; keep_states: also return the state every E-step started
+    from (beta, mu, sigma, eta) for state-injected ("teacher-forced") comparisons."""
     beta = np.array(beta0, dtype=np.float64)
+    if round_beta32:
+        beta = beta.astype(np.float32).astype(np.float64)
     K = beta.shape[-2]
     D = len(doc_ptr) - 1
     eta = np.zeros((D, K - 1))
     mu = np.zeros((D, K - 1))
     sigma = np.eye(K - 1) * 20.0
     gamma = None
-    bounds = []
+    bounds, states = [], []
     run = estep if estep_fn is None else estep_fn
     for it in range(100):
+        if keep_states:
+            states.append(dict(beta=beta.copy(), mu=mu.copy(), sigma=sigma.copy(), eta=eta.copy()))
         siginv, ent = prologue(sigma)
         r = run(doc_ptr, word_id, count, beta, mu, siginv, ent, eta, aspect=aspect)
         eta, theta = r["eta"], r["theta"]
@@ -227,11 +234,16 @@ def em(doc_ptr, word_id, count, beta0, X, n_iter, model="STM", mode="ols", sigpr
         mu, gamma = update_mu(eta, X, model, mode)
         sigma = update_sigma(eta, mu, r["sigma_ss"], sigprior)
         beta = update_beta(r["beta_ss"])
+        if round_beta32:
+            beta = beta.astype(np.float32).astype(np.float64)
         if it >= 1 and abs((bounds[-1] - bounds[-2]) / abs(bounds[-2])) < threshold:
             break
         if it == n_iter - 1:
             break
-    return dict(beta=beta, theta=theta, eta=eta, mu=mu, sigma=sigma, gamma=gamma, bounds=bounds)
+    out = dict(beta=beta, theta=theta, eta=eta, mu=mu, sigma=sigma, gamma=gamma, bounds=bounds)
+    if keep_states:
+        out["states"] = states
+    return out
 
 
 def eval_heldout(doc_ptr, word_id, count, theta, beta, return_doc_ll=False):

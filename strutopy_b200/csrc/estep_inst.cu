@@ -2,7 +2,6 @@
 // stm::post_kernel<STM_KPL>; compiled once per STM_KPL in {1,2,3,4} (K <= 32*STM_KPL) so the
 // instantiations build in parallel.
 #include "estep_kernel.cuh"
-#include "bfgs_slots.cuh"
 
 #ifndef STM_KPL
 #error "compile with -DSTM_KPL=1..4"
@@ -18,25 +17,6 @@ cudaError_t STM_CAT(stm_launch_bfgs_kpl, STM_KPL)(const stm::EstepParams& P, int
                                              cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
         if (e != cudaSuccess) return e;                                                               \
         stm::bfgs_kernel<STM_KPL, JJ><<<grid, block, smem, st>>>(P);                                  \
-        return cudaGetLastError();                                                                    \
-    }
-    switch (J) {
-        case 2: STM_LAUNCH(2)
-        case 4: STM_LAUNCH(4)
-        case 5: STM_LAUNCH(5)
-        default: STM_LAUNCH(8)
-    }
-#undef STM_LAUNCH
-}
-
-cudaError_t STM_CAT(stm_launch_bfgs_slots_kpl, STM_KPL)(const stm::EstepParams& P, int J, int grid, int block,
-                                                        size_t smem, cudaStream_t st) {
-#define STM_LAUNCH(JJ)                                                                                \
-    {                                                                                                 \
-        cudaError_t e = cudaFuncSetAttribute(stm::bfgs_slots_kernel<STM_KPL, JJ>,                     \
-                                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
-        if (e != cudaSuccess) return e;                                                               \
-        stm::bfgs_slots_kernel<STM_KPL, JJ><<<grid, block, smem, st>>>(P);                            \
         return cudaGetLastError();                                                                    \
     }
     switch (J) {

@@ -117,8 +117,6 @@ struct EstepParams {
     int smem_small;             // kernel A: bytes of the per-warp small block (K-vectors, line-search state)
     int tm_warps;               // kernel A: warps 0..tm_warps-1 keep their tile in TMEM (0, 4 or 8)
     int tm_cols;                // kernel A: TMEM columns per TMEM warp (512 or 256)
-    int tm_slots;               // kernel A (slots version, bfgs_slots.cuh): TMEM document slots per warp
-    int smem_tiles;             // kernel A (slots version): shared-memory document tiles per CTA
     unsigned long long* dbg_cycles;  // [8] phase cycle counters (only written when STM_DBG_TIMING)
 };
 #if STM_DBG_TIMING

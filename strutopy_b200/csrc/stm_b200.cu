@@ -3,7 +3,6 @@
 // include/stm_b200.h.  Reference behaviour cited per function (stm.py = /root/reference/src/modules/stm.py).
 #include "../../include/stm_b200.h"
 #include "estep_kernel.cuh"
-#include "bfgs_slots.cuh"
 
 #include <cublas_v2.h>
 #include <cusolverDn.h>
@@ -31,9 +30,6 @@ struct LengthClass {
     int post_warps = 0, post_smem_per_warp = 0, post_grid = 0;
     int post_groups = 0;   // > 0: group version of kernel B, this many documents per CTA
     int post_gw = 3;       //      warps per document there
-    // kernel A, slots version (bfgs_slots.cuh): warps per CTA, TMEM slots per warp, shared-memory tiles per CTA,
-    // bytes of a slot's small block, TMEM columns per slot, CTAs; s_warps == 0: not available for this class
-    int s_warps = 0, s_tm_slots = 0, s_tiles = 0, s_small = 0, s_tm_cols = 0, s_grid = 0;
 };
 
 }  // namespace
@@ -76,8 +72,8 @@ struct stm_ctx {
     cublasHandle_t cublas = nullptr;
     cusolverDnHandle_t cusolver = nullptr;
     int64_t launches = 0;
-    // stm_tune: kernel A version (1: document slots, 0: one warp per document) and its warps per CTA
-    int tune_bfgs_slots = 1, tune_bfgs_warps = 8;
+    // stm_tune: cap on kernel A's warps per CTA
+    int tune_bfgs_max_warps = STM_BFGS_MAX_THREADS / 32;
     cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};   // E-step phases: before kernel A, between, after kernel B
     cudaStream_t copy_stream = nullptr;                // host API: eta goes home while kernel B runs
     std::string err;
@@ -169,10 +165,6 @@ cudaError_t stm_launch_bfgs_kpl1(const stm::EstepParams&, int, int, int, size_t,
 cudaError_t stm_launch_bfgs_kpl2(const stm::EstepParams&, int, int, int, size_t, cudaStream_t);
 cudaError_t stm_launch_bfgs_kpl3(const stm::EstepParams&, int, int, int, size_t, cudaStream_t);
 cudaError_t stm_launch_bfgs_kpl4(const stm::EstepParams&, int, int, int, size_t, cudaStream_t);
-cudaError_t stm_launch_bfgs_slots_kpl1(const stm::EstepParams&, int, int, int, size_t, cudaStream_t);
-cudaError_t stm_launch_bfgs_slots_kpl2(const stm::EstepParams&, int, int, int, size_t, cudaStream_t);
-cudaError_t stm_launch_bfgs_slots_kpl3(const stm::EstepParams&, int, int, int, size_t, cudaStream_t);
-cudaError_t stm_launch_bfgs_slots_kpl4(const stm::EstepParams&, int, int, int, size_t, cudaStream_t);
 cudaError_t stm_launch_post_kpl1(const stm::EstepParams&, int, int, size_t, cudaStream_t);
 cudaError_t stm_launch_post_kpl2(const stm::EstepParams&, int, int, size_t, cudaStream_t);
 cudaError_t stm_launch_post_kpl3(const stm::EstepParams&, int, int, size_t, cudaStream_t);
@@ -192,43 +184,6 @@ cudaError_t launch_bfgs(int KPL, const stm::EstepParams& P, int J, int grid, int
         default: return stm_launch_bfgs_kpl4(P, J, grid, block, smem, st);
     }
 }
-cudaError_t launch_bfgs_slots(int KPL, const stm::EstepParams& P, int J, int grid, int block, size_t smem,
-                              cudaStream_t st) {
-    switch (KPL) {
-        case 1: return stm_launch_bfgs_slots_kpl1(P, J, grid, block, smem, st);
-        case 2: return stm_launch_bfgs_slots_kpl2(P, J, grid, block, smem, st);
-        case 3: return stm_launch_bfgs_slots_kpl3(P, J, grid, block, smem, st);
-        default: return stm_launch_bfgs_slots_kpl4(P, J, grid, block, smem, st);
-    }
-}
-// Slots version of kernel A (bfgs_slots.cuh): how many warps, TMEM slots per warp and shared-memory tiles fit.
-// A warp can only address its own 32-lane quarter of tensor memory; a quarter holds 2 documents of <= 256
-// columns or 1 of <= 512, so <= 4 warps take 2 TMEM slots each and 5..8 warps one.
-void config_slots(const stm_ctx* ctx, LengthClass& lc) {
-    const int K = ctx->K, TS = ctx->TS;
-    const int wslots = (lc.n_cap + 31) / 32, CS = (K + 1) & ~1;
-    int per_quarter = 0;
-    if (lc.n_cap <= 32 * lc.J) per_quarter = (wslots * CS <= 256) ? 2 : ((wslots * CS <= 512) ? 1 : 0);
-    int W = std::max(1, std::min(ctx->tune_bfgs_warps, STM_SLOTS_MAX_THREADS / 32));
-    int TW = 0;
-    if (per_quarter == 2) TW = (W <= 4) ? 2 : 1;
-    else if (per_quarter == 1) { TW = 1; W = std::min(W, 4); }
-    const size_t small_b = stm::slots_small_bytes(K, TS, lc.n_cap);
-    const size_t tile_b = stm::slots_tile_bytes(lc.n_cap, TS);
-    const long long avail = (long long)ctx->max_smem - 256 - (long long)W * TW * (long long)small_b;
-    int NS = avail > 0 ? (int)(avail / (long long)(small_b + tile_b)) : 0;
-    NS = std::min(NS, W * (stm::SLOT_GMAX - TW));
-    if (avail < 0) { lc.s_warps = 0; return; }
-    if (TW == 0) {
-        if (NS < 1) { lc.s_warps = 0; return; }
-        W = std::min(W, NS);
-    }
-    lc.s_warps = W; lc.s_tm_slots = TW; lc.s_tiles = NS; lc.s_small = (int)small_b;
-    lc.s_tm_cols = (per_quarter == 2) ? 256 : 512;
-    const int per_cta = W * TW + NS;
-    lc.s_grid = std::min(ctx->sm_count, (lc.n_docs + per_cta - 1) / per_cta);
-}
-
 cudaError_t launch_post(int KPL, const stm::EstepParams& P, int grid, int block, size_t smem, cudaStream_t st) {
     switch (KPL) {
         case 1: return stm_launch_post_kpl1(P, grid, block, smem, st);
@@ -672,15 +627,13 @@ int stm_estep_kernel_ms(stm_ctx* ctx, double* ms2) {
 }
 
 // Tuning interface (explicit; the library reads no environment variables).  Takes effect at the next
-// stm_set_corpus.  Keys: "bfgs_slots" (1: document-slot version of kernel A, 0: one warp per document),
-// "bfgs_warps" (warps per CTA of the slot version, 1..8).
+// stm_set_corpus.  Keys: "bfgs_max_warps" (cap on kernel A's warps = documents in flight per SM; occupancy studies).
 int stm_tune(stm_ctx* ctx, const char* key, int value) {
     if (!ctx || !key) return STM_ERR_INVALID;
     const std::string k(key);
-    if (k == "bfgs_slots") { ctx->tune_bfgs_slots = value ? 1 : 0; return STM_OK; }
-    if (k == "bfgs_warps") {
-        if (value < 1 || value > STM_SLOTS_MAX_THREADS / 32) return fail(ctx, STM_ERR_INVALID, "bfgs_warps must be in 1..8");
-        ctx->tune_bfgs_warps = value;
+    if (k == "bfgs_max_warps") {
+        if (value < 1) return fail(ctx, STM_ERR_INVALID, "bfgs_max_warps must be >= 1");
+        ctx->tune_bfgs_max_warps = value;
         return STM_OK;
     }
     return fail(ctx, STM_ERR_INVALID, "stm_tune: unknown key " + k);
@@ -801,7 +754,8 @@ int stm_set_corpus(stm_ctx* ctx, int64_t D, const int64_t* doc_ptr, const int32_
                 if (slots * CS <= 256) { lc.tm_warps = 8; lc.tm_cols = 256; }
                 else if (slots * CS <= 512) { lc.tm_warps = 4; lc.tm_cols = 512; }
             }
-            const int max_w = STM_BFGS_MAX_THREADS / 32;
+            const int max_w = std::min(STM_BFGS_MAX_THREADS / 32, ctx->tune_bfgs_max_warps);
+            lc.tm_warps = std::min(lc.tm_warps, max_w);
             const int avail = ctx->max_smem - 128 - lc.tm_warps * lc.smem_small;   // 128: static shared (TMEM base)
             int sw = avail > 0 ? avail / (lc.smem_small + lc.smem_per_warp) : 0;
             sw = std::max(0, std::min(sw, max_w - lc.tm_warps));
@@ -830,10 +784,6 @@ int stm_set_corpus(stm_ctx* ctx, int64_t D, const int64_t* doc_ptr, const int32_
             }
         }
         max_warps = std::max(max_warps, std::max(lc.grid * lc.warps, lc.post_grid * lc.post_warps));
-        if (ctx->tune_bfgs_slots) {
-            config_slots(ctx, lc);
-            max_warps = std::max(max_warps, lc.s_grid * lc.s_warps * stm::SLOT_GMAX);
-        }
         CU(cudaMalloc(&lc.d_docs, sizeof(int) * lc.n_docs));
         CU(cudaMemcpy(lc.d_docs, members[ci].data(), sizeof(int) * lc.n_docs, cudaMemcpyHostToDevice));
         max_warps = std::max(max_warps, lc.grid * lc.warps);
@@ -931,19 +881,10 @@ int stm_estep(stm_ctx* ctx, const float* beta_t_dev, const double* mu_dev, const
             P.scratch = ctx->d_scratch; P.scratch_stride = ctx->scratch_stride;
             P.n_cap = lc.n_cap; P.smem_per_warp = lc.smem_per_warp;
             P.smem_small = lc.smem_small; P.tm_warps = lc.tm_warps; P.tm_cols = lc.tm_cols;
-            P.tm_slots = 0; P.smem_tiles = 0;
             P.dbg_cycles = ctx->d_dbg;
             if (phase == 0) {
-                if (lc.s_warps > 0) {
-                    P.smem_small = lc.s_small; P.tm_slots = lc.s_tm_slots; P.smem_tiles = lc.s_tiles;
-                    P.tm_cols = lc.s_tm_cols;
-                    const size_t smem = (size_t)(lc.s_warps * lc.s_tm_slots + lc.s_tiles) * lc.s_small +
-                                        (size_t)lc.s_tiles * stm::slots_tile_bytes(lc.n_cap, ctx->TS);
-                    CU(launch_bfgs_slots(ctx->KPL, P, lc.J, lc.s_grid, lc.s_warps * 32, smem, st));
-                } else {
-                    CU(launch_bfgs(ctx->KPL, P, lc.J, lc.grid, lc.warps * 32,
-                                   (size_t)lc.smem_small * lc.warps + (size_t)lc.smem_per_warp * (lc.warps - lc.tm_warps), st));
-                }
+                CU(launch_bfgs(ctx->KPL, P, lc.J, lc.grid, lc.warps * 32,
+                               (size_t)lc.smem_small * lc.warps + (size_t)lc.smem_per_warp * (lc.warps - lc.tm_warps), st));
             } else {
                 P.smem_per_warp = lc.post_smem_per_warp;
                 if (lc.post_groups > 0) {

@@ -19,6 +19,18 @@ def load_golden(name):
         return {k: z[k] for k in z.files}
 
 
+def unpack_corpus(g, n_docs=None):
+    """CSR arrays of a fixture that stores its corpus compactly (doc_len uint16, word_id uint16, count uint8:
+    tests/golden/make_golden.py::pack_csr); optionally only the first n_docs documents."""
+    ln = g["doc_len"].astype(np.int64)
+    if n_docs is not None:
+        ln = ln[:n_docs]
+    ptr = np.zeros(len(ln) + 1, np.int64)
+    np.cumsum(ln, out=ptr[1:])
+    nnz = int(ptr[-1])
+    return ptr, g["word_id"][:nnz].astype(np.int32), g["count"][:nnz].astype(np.float64)
+
+
 @pytest.fixture(scope="session")
 def golden():
     return load_golden

@@ -13,7 +13,9 @@ Tolerances (DESIGN.md "Tolerances"): beta is stored in fp32 on the device, all a
 import numpy as np
 import pytest
 
-from conftest import load_golden, random_init_beta, synthetic_corpus
+import os
+
+from conftest import load_golden, random_init_beta, synthetic_corpus, unpack_corpus
 from oracle import c_oracle, stm_numpy
 
 pytestmark = pytest.mark.gpu
@@ -291,6 +293,108 @@ def test_em_trace_config1_vs_live_reference():
         np.testing.assert_allclose(m.beta, g["final_beta"], atol=1e-3)
         np.testing.assert_allclose(m.theta.sum(axis=1), 1.0, atol=1e-9)
         np.testing.assert_allclose(m.beta.sum(axis=1), 1.0, atol=1e-5)
+
+
+def _trace_rel(got, ref):
+    n = min(len(got), len(ref))
+    return np.abs((np.asarray(got[:n]) - np.asarray(ref[:n])) / np.asarray(ref[:n]))
+
+
+def _teacher_forced(m, ref, its, X, rel_tol=1e-9):
+    """State-injected comparison: the E-step + M-step from the ORACLE's state of EM iteration t must reproduce the oracle's
+    bound of that iteration and its M-step (every single step of the trajectory is faithful, free of the trajectory's
+    own amplification)."""
+    for t in its:
+        st = ref["states"][t]
+        m.beta, m.mu, m.sigma, m.eta = st["beta"], st["mu"], st["sigma"], st["eta"]
+        bss, sss = m.E_step()
+        assert abs(m.bound - ref["bounds"][t]) <= rel_tol * abs(ref["bounds"][t]), (t, m.bound, ref["bounds"][t])
+        if t + 1 < len(ref["states"]):
+            nxt = ref["states"][t + 1]
+            assert np.abs(m.eta - nxt["eta"]).max() <= 1e-6
+            m.M_step(bss, sss)
+            np.testing.assert_allclose(m.sigma, nxt["sigma"], rtol=1e-6, atol=1e-9)
+            np.testing.assert_allclose(m.mu, nxt["mu"], rtol=1e-6, atol=1e-8)
+            np.testing.assert_allclose(m.beta, nxt["beta"], rtol=2e-6, atol=1e-12)
+
+
+def test_em_trace_config2_cut_vs_live_reference():
+    """BASELINE.json configs[1] (K=20, V=5k, 2 prevalence covariates, 20 EM iterations) on the first 300 documents of
+    the reference-generated corpus: the CUDA path's ELBO trace against the LIVE reference's."""
+    from strutopy_b200 import STM
+    g = load_golden("em_c2.npz")
+    K, V, cut = int(g["K"]), int(g["V"]), int(g["cut"])
+    m = STM(unpack_corpus(g, cut), range(V), False, K, g["X"][:cut], False, 20, 0, 1e-5, init_type="random",
+            model_type="STM")
+    np.testing.assert_allclose(m.beta, g["cut_beta0"].astype(np.float32).astype(np.float64), rtol=0, atol=0)
+    m.expectation_maximization(saving=False)
+    assert len(m.last_bounds) == len(g["cut_bounds"]) == 20
+    rel = _trace_rel(m.last_bounds, g["cut_bounds"])
+    assert rel[:3].max() < 1e-6, rel
+    assert rel.max() < 1e-4, rel   # north-star tolerance, per iteration
+    np.testing.assert_allclose(m.gamma, g["cut_final_gamma"], atol=2e-2)
+    np.testing.assert_allclose(m.theta, g["cut_final_theta"], atol=5e-2)
+
+
+def test_em_trace_config2_full_size_vs_c_oracle():
+    """BASELINE.json configs[1] at full size (D=10k, V=5k, K=20, p=2, 20 EM iterations, 1 GPU): free-running ELBO trace
+    against the C oracle's EM (beta rounded to fp32 after every M-step, as the device stores it) <= 1e-4 per iteration,
+    and state-injected single steps along the oracle's trajectory <= 1e-9."""
+    from strutopy_b200 import STM
+    g = load_golden("em_c2.npz")
+    K, V = int(g["K"]), int(g["V"])
+    ptr, ids, cnt = unpack_corpus(g)
+    X = g["X"]
+    assert len(ptr) - 1 == 10000 and X.shape == (10000, 2)
+    nt = os.cpu_count() or 4
+    run = lambda *a, **k: c_oracle.estep(*a, nthreads=nt, **k)  # noqa: E731
+    ref = stm_numpy.em(ptr, ids, cnt, random_init_beta(K, V), X, n_iter=20, estep_fn=run, round_beta32=True,
+                       keep_states=True)
+    m = STM((ptr, ids, cnt), range(V), False, K, X, False, 20, 0, 1e-5, init_type="random", model_type="STM")
+    m.expectation_maximization(saving=False)
+    assert len(m.last_bounds) == len(ref["bounds"]), (len(m.last_bounds), len(ref["bounds"]))
+    rel = _trace_rel(m.last_bounds, ref["bounds"])
+    assert rel[:4].max() < 1e-9, rel
+    assert rel.max() < 1e-4, rel
+    np.testing.assert_allclose(m.gamma, ref["gamma"], atol=1e-2)
+    np.testing.assert_allclose(m.sigma, ref["sigma"], atol=1e-2)
+    _teacher_forced(m, ref, (0, 1, 7, 13, len(ref["bounds"]) - 1), X)
+
+
+def test_em_trace_k50_spectral_vs_live_reference_and_c_oracle():
+    """K=50 from a spectral initialisation, 25 EM iterations (BASELINE config 3's regime at oracle-sized D).
+
+    Measured fact about the REFERENCE (tests/test_oracle_golden.py::test_em_k50_cut_trace_c_oracle, DESIGN.md §5): at
+    K=50 its EM map is not only expansive (~3x per iteration) but discontinuous — a borderline PD test / line-search
+    branch in one document moves the ELBO by ~1e-3 — so two faithful fp64 implementations (the C oracle and SciPy's own
+    driver, 1e-14 apart after the first E-step) are 1e-3 apart by iteration 16.  A free-running 25-iteration trace can
+    therefore be held to 1e-4 only while the perturbation is still below the branch threshold; what CAN be held is
+    (i) the early trace, and (ii) every single step along the oracle's trajectory (state-injected), to 1e-9."""
+    from strutopy_b200 import STM
+    g = load_golden("em_k50.npz")
+    K, V, cut = int(g["K"]), int(g["V"]), int(g["cut"])
+    beta0 = g["beta0"].astype(np.float64)
+    # (a) the live reference's trace on the first 200 documents
+    m = STM(unpack_corpus(g, cut), range(V), False, K, g["X"][:cut], False, 25, 0, 1e-5, init_type="random",
+            model_type="STM")
+    m.beta = beta0
+    m.expectation_maximization(saving=False)
+    rel = _trace_rel(m.last_bounds, g["cut_bounds"])
+    assert rel[:8].max() < 1e-7, rel
+    assert rel[:14].max() < 1e-4, rel
+    assert rel.max() < 5e-3, rel
+    # (b) D=2000: free-running against the C oracle, then state-injected steps along the oracle's trajectory
+    ptr, ids, cnt = unpack_corpus(g)
+    nt = os.cpu_count() or 4
+    run = lambda *a, **k: c_oracle.estep(*a, nthreads=nt, **k)  # noqa: E731
+    ref = stm_numpy.em(ptr, ids, cnt, beta0, g["X"], n_iter=25, estep_fn=run, round_beta32=True, keep_states=True)
+    m = STM((ptr, ids, cnt), range(V), False, K, g["X"], False, 25, 0, 1e-5, init_type="random", model_type="STM")
+    m.beta = beta0
+    m.expectation_maximization(saving=False)
+    rel = _trace_rel(m.last_bounds, ref["bounds"])
+    assert rel[:6].max() < 1e-8, rel
+    assert rel.max() < 5e-3, rel
+    _teacher_forced(m, ref, (0, 1, 5, 10, 15, 20, len(ref["bounds"]) - 1), g["X"])
 
 
 def test_em_trace_toy_ctm_vs_live_reference():
