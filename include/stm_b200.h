@@ -154,6 +154,11 @@ int stm_estep_host(stm_ctx* ctx, const double* beta, const double* mu, const dou
 int stm_heldout(stm_ctx* ctx, int64_t D, const int64_t* doc_ptr_dev, const int32_t* word_id_dev,
                 const float* count_dev, const double* theta_dev, const float* beta_t_dev,
                 double* doc_ll_dev, double* mean_dev, void* stream);
+/* as stm_heldout, with the fit's fp64 master copy of beta (word-major double [V][TS], the beta64_t buffer stm_mstep
+ * fills): the reference scores with its float64 beta, and an M-step entry below the fp32 range must not become log(0) */
+int stm_heldout64(stm_ctx* ctx, int64_t D, const int64_t* doc_ptr_dev, const int32_t* word_id_dev,
+                  const float* count_dev, const double* theta_dev, const double* beta64_t_dev,
+                  double* doc_ll_dev, double* mean_dev, void* stream);
 int stm_heldout_host(stm_ctx* ctx, int64_t D, const int64_t* doc_ptr, const int32_t* word_id,
                      const float* count, const double* theta, const double* beta_kv, double* doc_ll,
                      double* mean);

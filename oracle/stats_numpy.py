@@ -6,6 +6,16 @@ what `stm_moments` packs per shard and what `stm_mstep` computes from the all-re
 import numpy as np
 
 
+def stats_layout(A, V, TS, K, p):
+    """Python mirror of stm_stats_layout (include/stm_b200.h): segment offsets + total length (CPU tests)."""
+    K1 = K - 1
+    sizes = [A * V * TS, K1 * K1, 1, 1, K1, p, p * p, p * K1, K1 * K1]
+    off = [0]
+    for s in sizes:
+        off.append(off[-1] + s)
+    return off
+
+
 def pack_stats(off, beta_ss_t, sigma_ss, bound, n_docs, eta, X):
     """Build the packed fp64 statistics vector of one shard on the host (test helper / spec):
     segments as documented in include/stm_b200.h."""

@@ -16,7 +16,7 @@ EXPORTS = [
     "stm_create", "stm_destroy", "stm_last_error", "stm_beta_stride", "stm_launch_count", "stm_estep_kernel_ms",
     "stm_tune",
     "stm_set_corpus", "stm_stats_layout", "stm_prologue", "stm_estep", "stm_moments", "stm_mstep",
-    "stm_beta_to_wordmajor", "stm_wordmajor_to_kv", "stm_estep_host", "stm_heldout", "stm_heldout_host",
+    "stm_beta_to_wordmajor", "stm_wordmajor_to_kv", "stm_estep_host", "stm_heldout", "stm_heldout64", "stm_heldout_host",
     "stm_spectral_gram", "stm_spectral_finish", "stm_sample_corpus", "stm_update_kappa",
 ]
 
@@ -53,6 +53,7 @@ def load():
     L.stm_estep_kernel_ms.argtypes = [vp, C.POINTER(C.c_double)]
     L.stm_tune.argtypes = [vp, C.c_char_p, i32]
     L.stm_heldout.argtypes = [vp, i64, vp, vp, vp, vp, vp, vp, vp, vp]
+    L.stm_heldout64.argtypes = [vp, i64, vp, vp, vp, vp, vp, vp, vp, vp]
     L.stm_heldout_host.argtypes = [vp, i64, vp, vp, vp, vp, vp, vp, C.POINTER(C.c_double)]
     L.stm_spectral_gram.argtypes = [vp, i32, vp, vp, vp]
     L.stm_spectral_finish.argtypes = [vp, i32, vp, vp, vp, vp, vp, vp]

@@ -158,7 +158,7 @@ int stm_sample_corpus(stm_ctx* ctx, int64_t D, int n_words, const double* theta_
         !count_dev || !nnz_out)
         return fail(ctx, STM_ERR_INVALID, "stm_sample_corpus: bad arguments (1 <= n_words <= 4096)");
     if (D > 0x7fffffffLL) return fail(ctx, STM_ERR_UNSUPPORTED, "stm_sample_corpus: more than 2^31 documents");
-    CU(cudaSetDevice(ctx->device));
+    STM_ON_DEVICE(ctx);
     cudaStream_t st = (cudaStream_t)stream;
     const int K = ctx->K, V = ctx->V;
     int npow2 = 2;

@@ -314,7 +314,7 @@ int stm_update_kappa(stm_ctx* ctx, const double* stats_dev, const double* logm_d
     if (A < 2) return fail(ctx, STM_ERR_UNSUPPORTED, "stm_update_kappa: the content model needs A >= 2 aspects");
     if (A > AMAX) return fail(ctx, STM_ERR_UNSUPPORTED, "stm_update_kappa: more than 8 content levels");
     if (word_column >= V) return fail(ctx, STM_ERR_INVALID, "stm_update_kappa: word_column out of range");
-    CU(cudaSetDevice(ctx->device));
+    STM_ON_DEVICE(ctx);
     cudaStream_t st = (cudaStream_t)stream;
     double* lin = nullptr; int* d_flag = nullptr;
     auto cleanup = [&]() { cudaFree(lin); cudaFree(d_flag); };

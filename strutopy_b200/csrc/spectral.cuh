@@ -483,7 +483,7 @@ int stm_spectral_gram(stm_ctx* ctx, int n_keep, const int32_t* keep, double* gra
     if (!ctx->d_doc_ptr) return fail(ctx, STM_ERR_NO_CORPUS, "stm_spectral_gram: stm_set_corpus has not been called");
     if (n_keep < 1 || n_keep > ctx->V || !keep || !gram_dev)
         return fail(ctx, STM_ERR_INVALID, "stm_spectral_gram: bad keep list or NULL output");
-    CU(cudaSetDevice(ctx->device));
+    STM_ON_DEVICE(ctx);
     cudaStream_t st = (cudaStream_t)stream;
     const int n = n_keep;
     std::vector<int> col_of(ctx->V, -1);
@@ -552,7 +552,7 @@ int stm_spectral_finish(stm_ctx* ctx, int n_keep, const int32_t* keep, const dou
     if (n < 1 || n > V || !keep || !wprob_keep || !gram_dev || !beta_kv_dev)
         return fail(ctx, STM_ERR_INVALID, "stm_spectral_finish: bad arguments");
     if (K > n) return fail(ctx, STM_ERR_INVALID, "stm_spectral_finish: more topics than kept words");
-    CU(cudaSetDevice(ctx->device));
+    STM_ON_DEVICE(ctx);
     cudaStream_t st = (cudaStream_t)stream;
     const int nstrips = (n + STRIP - 1) / STRIP;
     const dim3 sgrid(nstrips, (n + 256 * CPT - 1) / (256 * CPT));

@@ -81,6 +81,24 @@ struct stm_ctx {
 
 namespace {
 
+// Every C-ABI entry runs on the context's device and puts the caller's current device back on return (a caller with
+// two contexts, or torch's notion of the current device, must not be disturbed).
+struct DeviceGuard {
+    int prev = -1;
+    bool ok = true;
+    explicit DeviceGuard(int dev) {
+        if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+        if (prev != dev) ok = (cudaSetDevice(dev) == cudaSuccess);
+        else prev = -1;
+    }
+    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+    DeviceGuard(const DeviceGuard&) = delete;
+    DeviceGuard& operator=(const DeviceGuard&) = delete;
+};
+#define STM_ON_DEVICE(ctx)                                                                     \
+    DeviceGuard dev_guard_((ctx)->device);                                                     \
+    if (!dev_guard_.ok) return fail((ctx), STM_ERR_CUDA, "cudaSetDevice failed")
+
 int fail(stm_ctx* c, int code, const std::string& msg) {
     if (c) c->err = msg; else g_create_error = msg;
     return code;
@@ -617,7 +635,7 @@ int64_t stm_launch_count(const stm_ctx* ctx) { return ctx ? ctx->launches : 0; }
 
 int stm_estep_kernel_ms(stm_ctx* ctx, double* ms2) {
     if (!ctx || !ms2) return STM_ERR_INVALID;
-    CU(cudaSetDevice(ctx->device));
+    STM_ON_DEVICE(ctx);
     CU(cudaEventSynchronize(ctx->ev[2]));
     float a = 0.f, b = 0.f;
     CU(cudaEventElapsedTime(&a, ctx->ev[0], ctx->ev[1]));
@@ -650,8 +668,9 @@ int stm_create(int device, int K, int V, int A, stm_ctx** out) {
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
         return fail(ctx, STM_ERR_CUDA, "no CUDA device available (this library has no CPU fallback)");
     if (device < 0 || device >= ndev) return fail(ctx, STM_ERR_INVALID, "bad device index");
-    cudaError_t e = cudaSetDevice(device);
-    if (e != cudaSuccess) return fail(ctx, STM_ERR_CUDA, cudaGetErrorString(e));
+    DeviceGuard guard(device);
+    if (!guard.ok) return fail(ctx, STM_ERR_CUDA, "cudaSetDevice failed");
+    cudaError_t e;
     cudaDeviceProp prop;
     e = cudaGetDeviceProperties(&prop, device);
     if (e != cudaSuccess) return fail(ctx, STM_ERR_CUDA, cudaGetErrorString(e));
@@ -686,7 +705,7 @@ int stm_create(int device, int K, int V, int A, stm_ctx** out) {
 
 void stm_destroy(stm_ctx* c) {
     if (!c) return;
-    cudaSetDevice(c->device);
+    DeviceGuard guard(c->device);
     free_corpus(c);
     cudaFree(c->d_msmall); cudaFree(c->d_info); cudaFree(c->d_potrf_work); cudaFree(c->d_syevd_work);
     if (c->cublas) cublasDestroy(c->cublas);
@@ -700,7 +719,7 @@ int stm_set_corpus(stm_ctx* ctx, int64_t D, const int64_t* doc_ptr, const int32_
                    const int32_t* aspect) {
     if (!ctx) return STM_ERR_INVALID;
     if (D < 0 || !doc_ptr) return fail(ctx, STM_ERR_INVALID, "documents must be specified to establish input space");
-    CU(cudaSetDevice(ctx->device));
+    STM_ON_DEVICE(ctx);
     if (doc_ptr[0] != 0) return fail(ctx, STM_ERR_INVALID, "doc_ptr[0] must be 0");
     const int64_t nnz = doc_ptr[D];
     int n_max = 0;
@@ -715,10 +734,8 @@ int stm_set_corpus(stm_ctx* ctx, int64_t D, const int64_t* doc_ptr, const int32_
         for (int64_t d = 0; d < D; ++d)
             if (aspect[d] < 0 || aspect[d] >= ctx->A) return fail(ctx, STM_ERR_INVALID, "aspect out of range [0, A)");
     }
-    free_corpus(ctx);
-    ctx->D = D; ctx->nnz = nnz; ctx->n_max = n_max;
-
     // ---- length classes: tile capacity per warp -> warps per CTA -------------------------------
+    // (all validation happens BEFORE the previous corpus is released: a failing call leaves the context as it was)
     const int caps[] = {64, 128, 160, 256, 384, 512, 768, 1024, 1536, 2048, 3072, 4096, 6144, 8192};
     const int ncaps = (int)(sizeof(caps) / sizeof(caps[0]));
     std::vector<std::vector<int>> members(ncaps);
@@ -731,6 +748,8 @@ int stm_set_corpus(stm_ctx* ctx, int64_t D, const int64_t* doc_ptr, const int32_
         members[ci].push_back((int)d);
     }
     int max_warps = 0;
+    std::vector<LengthClass> new_classes;
+    std::vector<int> class_of;   // index into members[] of every new class
     for (int ci = 0; ci < ncaps; ++ci) {
         if (members[ci].empty()) continue;
         LengthClass lc;
@@ -784,9 +803,16 @@ int stm_set_corpus(stm_ctx* ctx, int64_t D, const int64_t* doc_ptr, const int32_
             }
         }
         max_warps = std::max(max_warps, std::max(lc.grid * lc.warps, lc.post_grid * lc.post_warps));
+        new_classes.push_back(lc);
+        class_of.push_back(ci);
+    }
+    // everything is validated: release the previous corpus and take the new one
+    free_corpus(ctx);
+    ctx->D = D; ctx->nnz = nnz; ctx->n_max = n_max;
+    for (size_t i = 0; i < new_classes.size(); ++i) {
+        LengthClass& lc = new_classes[i];
         CU(cudaMalloc(&lc.d_docs, sizeof(int) * lc.n_docs));
-        CU(cudaMemcpy(lc.d_docs, members[ci].data(), sizeof(int) * lc.n_docs, cudaMemcpyHostToDevice));
-        max_warps = std::max(max_warps, lc.grid * lc.warps);
+        CU(cudaMemcpy(lc.d_docs, members[class_of[i]].data(), sizeof(int) * lc.n_docs, cudaMemcpyHostToDevice));
         ctx->classes.push_back(lc);
     }
     CU(cudaMalloc(&ctx->d_doc_ptr, sizeof(long long) * (D + 1)));
@@ -835,7 +861,7 @@ int stm_stats_layout(const stm_ctx* ctx, int p, int64_t* offsets) {
 int stm_prologue(stm_ctx* ctx, const double* sigma_dev, double* prior_dev, int* info_dev, void* stream) {
     if (!ctx || !sigma_dev || !prior_dev || !info_dev) return STM_ERR_INVALID;
     cudaStream_t st = (cudaStream_t)stream;
-    CU(cudaSetDevice(ctx->device));
+    STM_ON_DEVICE(ctx);
     const int K1 = ctx->K1;
     double* L = ctx->d_msmall;  // K1*K1
     CU(cudaMemcpyAsync(L, sigma_dev, sizeof(double) * K1 * K1, cudaMemcpyDeviceToDevice, st));
@@ -856,7 +882,7 @@ int stm_estep(stm_ctx* ctx, const float* beta_t_dev, const double* mu_dev, const
         !doc_info_dev || !doc_nfev_dev)
         return fail(ctx, STM_ERR_INVALID, "NULL device pointer passed to stm_estep");
     cudaStream_t st = (cudaStream_t)stream;
-    CU(cudaSetDevice(ctx->device));
+    STM_ON_DEVICE(ctx);
     int64_t off[10];
     layout(ctx, 0, off);
     const int K1 = ctx->K1;
@@ -915,7 +941,7 @@ int stm_moments(stm_ctx* ctx, const double* eta_dev, const double* x_dev, int p,
     if (!ctx || !eta_dev || !stats_dev || p < 0 || (p > 0 && !x_dev)) return STM_ERR_INVALID;
     if (!ctx->d_doc_ptr) return fail(ctx, STM_ERR_NO_CORPUS, "stm_set_corpus has not been called");
     cudaStream_t st = (cudaStream_t)stream;
-    CU(cudaSetDevice(ctx->device));
+    STM_ON_DEVICE(ctx);
     CB(cublasSetStream(ctx->cublas, st));
     int64_t off[10];
     layout(ctx, p, off);
@@ -954,7 +980,7 @@ int stm_mstep(stm_ctx* ctx, const double* stats_dev, const double* x_dev, int p,
     if (model == STM_MODEL_STM && (p < 1 || !x_dev || !gamma_t_dev))
         return fail(ctx, STM_ERR_INVALID, "STM mode needs a design matrix with p >= 1 and a gamma buffer");
     cudaStream_t st = (cudaStream_t)stream;
-    CU(cudaSetDevice(ctx->device));
+    STM_ON_DEVICE(ctx);
     CB(cublasSetStream(ctx->cublas, st));
     CS(cusolverDnSetStream(ctx->cusolver, st));
     const int K1 = ctx->K1, K = ctx->K, V = ctx->V, TS = ctx->TS;
@@ -1034,7 +1060,7 @@ int stm_mstep(stm_ctx* ctx, const double* stats_dev, const double* x_dev, int p,
 
 int stm_beta_to_wordmajor(stm_ctx* ctx, const double* beta_kv_dev, float* beta_t_dev, void* stream) {
     if (!ctx || !beta_kv_dev || !beta_t_dev) return STM_ERR_INVALID;
-    CU(cudaSetDevice(ctx->device));
+    STM_ON_DEVICE(ctx);
     beta_to_wordmajor_kernel<<<ctx->sm_count * 4, 256, 0, (cudaStream_t)stream>>>(beta_kv_dev, beta_t_dev, ctx->A,
                                                                                   ctx->K, ctx->V, ctx->TS);
     ctx->launches++;
@@ -1043,7 +1069,7 @@ int stm_beta_to_wordmajor(stm_ctx* ctx, const double* beta_kv_dev, float* beta_t
 }
 int stm_wordmajor_to_kv(stm_ctx* ctx, const double* src_t_dev, double* dst_kv_dev, void* stream) {
     if (!ctx || !src_t_dev || !dst_kv_dev) return STM_ERR_INVALID;
-    CU(cudaSetDevice(ctx->device));
+    STM_ON_DEVICE(ctx);
     wordmajor_to_kv_kernel<<<ctx->sm_count * 4, 256, 0, (cudaStream_t)stream>>>(src_t_dev, dst_kv_dev, ctx->A, ctx->K,
                                                                                 ctx->V, ctx->TS);
     ctx->launches++;
@@ -1058,7 +1084,7 @@ int stm_estep_host(stm_ctx* ctx, const double* beta, const double* mu, const dou
     if (!ctx->d_doc_ptr) return fail(ctx, STM_ERR_NO_CORPUS, "stm_set_corpus has not been called");
     if (!beta || !mu || !siginv || !eta || !theta || !beta_ss || !sigma_ss || !bound)
         return fail(ctx, STM_ERR_INVALID, "NULL host pointer passed to stm_estep_host");
-    CU(cudaSetDevice(ctx->device));
+    STM_ON_DEVICE(ctx);
     const int K = ctx->K, K1 = ctx->K1, V = ctx->V, A = ctx->A, TS = ctx->TS;
     const int64_t D = ctx->D;
     // the reference's siginv is diagonal by construction (stm.py:501: element-wise product of a lower- and
@@ -1141,9 +1167,21 @@ int stm_heldout(stm_ctx* ctx, int64_t D, const int64_t* doc_ptr_dev, const int32
     if (D < 1 || !doc_ptr_dev || !word_id_dev || !count_dev || !theta_dev || !beta_t_dev || !doc_ll_dev || !mean_dev)
         return fail(ctx, STM_ERR_INVALID, "stm_heldout: NULL pointer or no documents");
     if (ctx->A != 1) return fail(ctx, STM_ERR_UNSUPPORTED, "stm_heldout: eval_heldout takes one K x V beta (A = 1)");
-    CU(cudaSetDevice(ctx->device));
+    STM_ON_DEVICE(ctx);
     return heldout_launch<float>(ctx, D, doc_ptr_dev, word_id_dev, count_dev, theta_dev, beta_t_dev, doc_ll_dev,
                                  mean_dev, (cudaStream_t)stream);
+}
+
+int stm_heldout64(stm_ctx* ctx, int64_t D, const int64_t* doc_ptr_dev, const int32_t* word_id_dev,
+                  const float* count_dev, const double* theta_dev, const double* beta64_t_dev, double* doc_ll_dev,
+                  double* mean_dev, void* stream) {
+    if (!ctx) return STM_ERR_INVALID;
+    if (D < 1 || !doc_ptr_dev || !word_id_dev || !count_dev || !theta_dev || !beta64_t_dev || !doc_ll_dev || !mean_dev)
+        return fail(ctx, STM_ERR_INVALID, "stm_heldout64: NULL pointer or no documents");
+    if (ctx->A != 1) return fail(ctx, STM_ERR_UNSUPPORTED, "stm_heldout64: eval_heldout takes one K x V beta (A = 1)");
+    STM_ON_DEVICE(ctx);
+    return heldout_launch<double>(ctx, D, doc_ptr_dev, word_id_dev, count_dev, theta_dev, beta64_t_dev, doc_ll_dev,
+                                  mean_dev, (cudaStream_t)stream);
 }
 
 int stm_heldout_host(stm_ctx* ctx, int64_t D, const int64_t* doc_ptr, const int32_t* word_id, const float* count,
@@ -1159,7 +1197,7 @@ int stm_heldout_host(stm_ctx* ctx, int64_t D, const int64_t* doc_ptr, const int3
         if (doc_ptr[d + 1] < doc_ptr[d]) return fail(ctx, STM_ERR_INVALID, "doc_ptr must be non-decreasing");
     for (int64_t i = 0; i < nnz; ++i)
         if (word_id[i] < 0 || word_id[i] >= ctx->V) return fail(ctx, STM_ERR_INVALID, "word id out of range [0, V)");
-    CU(cudaSetDevice(ctx->device));
+    STM_ON_DEVICE(ctx);
     const int K = ctx->K, V = ctx->V, TS = ctx->TS;
     long long* d_ptr = nullptr; int* d_ids = nullptr; float* d_cnt = nullptr;
     double *d_theta = nullptr, *d_bkv = nullptr, *d_bt = nullptr, *d_ll = nullptr;

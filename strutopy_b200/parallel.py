@@ -29,21 +29,11 @@ def shard_bounds(doc_ptr, world):
     return [(cuts[r], cuts[r + 1]) for r in range(world)]
 
 
-def stats_layout(A, V, TS, K, p):
-    """Python mirror of stm_stats_layout (include/stm_b200.h): segment offsets + total length."""
-    K1 = K - 1
-    sizes = [A * V * TS, K1 * K1, 1, 1, K1, p, p * p, p * K1, K1 * K1]
-    off = [0]
-    for s in sizes:
-        off.append(off[-1] + s)
-    return off
-
-
 def allreduce_stats(stats, dist=None):
-    """The one collective of an EM iteration.  `stats` is a torch tensor (CUDA with NCCL, CPU with
-    gloo); reduced in place and returned."""
-    if dist is None:
-        import torch.distributed as dist  # noqa: PLW0642
-    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+    """THE collective of the data-parallel path: a sum-all-reduce, in place, of a torch tensor (CUDA with NCCL on the
+    GPU box, CPU with gloo in the tests).  Every exchange of the product goes through here: the packed statistics
+    buffer once per EM iteration (STM._reduce_and_bound), the moments in M_step(), the Gram statistics of the
+    spectral initialisation, document / word totals in the constructor.  `dist` None (single process): no-op."""
+    if dist is not None and dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
         dist.all_reduce(stats, op=dist.ReduceOp.SUM)
     return stats

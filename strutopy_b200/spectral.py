@@ -45,11 +45,11 @@ def spectral_on_context(ctx, torch, dev, word_totals, maxV=5000, dist=None, retu
         err = e
     if dist is not None:
         bad = torch.tensor([1 if err is not None else 0], dtype=torch.int32, device=dev)
-        dist.all_reduce(bad)
+        allreduce_stats(bad, dist)
         if int(bad.item()) and err is None:
             err = _lib.StmError(_lib.STM_ERR_INVALID, "Encountered zeroes in Q row sums, can not normalize. (another rank)")
         if err is None:
-            dist.all_reduce(gram)
+            allreduce_stats(gram, dist)
     if err is not None:
         _raise(err)
     beta = torch.empty((ctx.K, ctx.V), dtype=torch.float64, device=dev)

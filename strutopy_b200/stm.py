@@ -6,11 +6,17 @@ through libstm_b200.so (include/stm_b200.h).  PyTorch tensors are only the owner
 device; `beta`, `eta`, `theta`, `mu`, `sigma`, `gamma` are host views fetched on access and uploaded
 on assignment, so reference-style state injection (`model.beta = ...`) keeps working.
 
-New keyword arguments (all optional, defaults reproduce the reference): `device`; `distributed`
-(shard the documents over the ranks of the initialised torch.distributed group); `presharded`
-(with `distributed`: `documents`, `X`, `beta_index` already are this rank's shard); `mnreg_column`
-(content model, `lda_beta=False`: None regresses word v on its own count column; 1 reproduces the reference
-AS WRITTEN, whose `mnreg` regresses every word on column 1, stm.py:825 — DESIGN.md §10.4).
+New keyword arguments (all optional): `device`; `distributed` (shard the documents over the ranks of the
+initialised torch.distributed group); `presharded` (with `distributed`: `documents`, `X`, `beta_index` already are
+this rank's shard).  Their defaults reproduce the reference.  ONE default deviates from the reference on purpose:
+`mnreg_column` (content model, `lda_beta=False` only).  The reference's `mnreg` regresses EVERY word on count column 1
+(stm.py:825), which makes beta collapse to the unigram distribution, and it raises on SciPy >= 1.14; the default
+`mnreg_column=None` regresses word v on its own column (the minimal repair, logged as a warning on first use, pinned
+against the oracle in tests/test_mnreg.py::test_gpu_kappa_own_column_vs_oracle_and_fit); `mnreg_column=1` reproduces
+the reference AS WRITTEN (pinned against the live reference) — DESIGN.md §10.4.
+
+The array attributes are read-only snapshots: assign the whole attribute (`model.eta = new`) to change device state;
+an in-place edit (`model.eta[i] = x`) raises instead of silently changing only the host copy.
 """
 import logging
 import os
@@ -22,7 +28,7 @@ import numpy as np
 
 from . import _lib
 from .corpus import pack_corpus, word_counts
-from .parallel import shard_bounds
+from .parallel import allreduce_stats, shard_bounds
 
 logger = logging.getLogger(__name__)
 
@@ -129,7 +135,7 @@ class STM:
         if self._dist is not None and presharded:
             lo, hi = 0, self.N
             cnt_t = torch.tensor([self.N], dtype=torch.int64, device=self._dev)
-            self._dist.all_reduce(cnt_t)
+            allreduce_stats(cnt_t, self._dist)
             self._presharded_total = int(cnt_t.item())
         else:
             lo, hi = shard_bounds(ptr, self.world)[self.rank]
@@ -160,6 +166,9 @@ class STM:
         self._off = self._ctx.stats_layout(self._p)
         self._d = dict(
             beta_t=torch.zeros((nA, self.V, TS), dtype=torch.float32, device=self._dev),
+            # fp64 master copy of beta (word-major like beta_t): what `beta`, save_model and eval_heldout report;
+            # the E-step kernels read the fp32 copy (north-star storage format)
+            beta64_t=torch.zeros((nA, self.V, TS), dtype=torch.float64, device=self._dev),
             mu=torch.zeros((Dl, K1), **f64),
             eta=torch.zeros((Dl, K1), **f64),
             theta=torch.zeros((Dl, self.K), **f64),
@@ -174,7 +183,7 @@ class STM:
             gamma_t=torch.zeros((max(self._p, 1), K1), **f64),
         )
         self._host = {}
-        self.gamma = None
+        self._have_gamma = False
         self.init_params()
 
     # ------------------------------------------------------------------------------------------------
@@ -198,11 +207,18 @@ class STM:
         self._dist.all_gather_object(parts, t.cpu().numpy())
         return np.concatenate(parts, axis=0)
 
+    def _ro(self, a):
+        """host views are snapshots of device state: read-only, so that an in-place edit (model.eta[i] = x) raises
+        instead of silently changing only the cache — assign the whole attribute to change device state"""
+        a.setflags(write=False)
+        return a
+
     @property
     def beta(self):
+        """K x V (A x K x V with a content covariate) float64 — the fp64 master copy the M-step writes"""
         if "beta" not in self._host:
-            b = self._d["beta_t"][:, :, :self.K].permute(0, 2, 1).to(self._torch.float64).cpu().numpy()
-            self._host["beta"] = b if self._use_aspect else b[0]
+            b = self._d["beta64_t"][:, :, :self.K].permute(0, 2, 1).contiguous().cpu().numpy()
+            self._host["beta"] = self._ro(b if self._use_aspect else b[0])
         return self._host["beta"]
 
     @beta.setter
@@ -210,14 +226,25 @@ class STM:
         torch = self._torch
         b = np.asarray(value, dtype=np.float64).reshape(self._nA, self.K, self.V)
         src = torch.from_numpy(np.ascontiguousarray(b)).to(self._dev)
+        self._d["beta64_t"].zero_()
+        self._d["beta64_t"][:, :, :self.K].copy_(src.permute(0, 2, 1))
         _lib.check(self._ctx.handle, _lib.load().stm_beta_to_wordmajor(
             self._ctx.handle, src.data_ptr(), self._ptr("beta_t"), self._stream()))
         torch.cuda.current_stream(self._dev).synchronize()
         self._invalidate("beta")
 
+    @property
+    def gamma(self):
+        """K-1 x p prevalence coefficients (stm.py:703); None before the first M-step, as in the reference"""
+        if not self._have_gamma:
+            return None
+        if "gamma" not in self._host:
+            self._host["gamma"] = self._ro(self._d["gamma_t"][:self._p].t().contiguous().cpu().numpy())
+        return self._host["gamma"]
+
     def _get_rows(self, name):
         if name not in self._host:
-            self._host[name] = self._gather_rows(self._d[name])
+            self._host[name] = self._ro(self._gather_rows(self._d[name]))
         return self._host[name]
 
     def _set_rows(self, name, value, cols):
@@ -236,7 +263,7 @@ class STM:
     @property
     def sigma(self):
         if "sigma" not in self._host:
-            self._host["sigma"] = self._d["sigma"].cpu().numpy()
+            self._host["sigma"] = self._ro(self._d["sigma"].cpu().numpy())
         return self._host["sigma"]
 
     @sigma.setter
@@ -263,7 +290,7 @@ class STM:
             totals = np.asarray(self.wcounts, dtype=np.float64)
             if self._presharded_total is not None:
                 t = self._torch.from_numpy(totals.copy()).to(self._dev)
-                self._dist.all_reduce(t)
+                allreduce_stats(t, self._dist)
                 totals = t.cpu().numpy()
             width = int(np.flatnonzero(totals).max()) + 1 if np.any(totals) else 1   # create_dtm's width, stm.py:119
             b = spectral_on_context(self._ctx, self._torch, self._dev, totals[:width], maxV=5000, dist=self._dist)
@@ -308,18 +335,22 @@ class STM:
                                   self._ptr("doc_info"), self._ptr("doc_nfev"), st))
         self._invalidate("eta", "theta")
 
+    def _allreduce(self, t):
+        """the ONE collective of an EM iteration (and of M_step / the spectral Gram): sum over the document shards"""
+        allreduce_stats(t, self._dist)
+
     def _reduce_and_bound(self):
-        """moments, the one all-reduce of the packed statistics, and the ELBO (synchronises)."""
+        """moments, the one all-reduce of the packed statistics, and the ELBO — the ONE host synchronisation of an
+        EM iteration (a Sigma that is not positive definite makes the prior, hence the bound, NaN: the Cholesky status
+        is only fetched then)."""
         L, h, st = _lib.load(), self._ctx.handle, self._stream()
         _lib.check(h, L.stm_moments(h, self._ptr("eta"), self._ptr("x"), self._p, self._ptr("stats"), st))
-        if self._dist is not None:
-            self._dist.all_reduce(self._d["stats"])
-        head = self._d["stats"][self._off[2]:self._off[2] + 2].cpu().numpy()
-        info = int(self._d["info"][0].item())
-        if info != 0:
+        self._allreduce(self._d["stats"])
+        bound = float(self._d["stats"][self._off[2]].item())
+        if bound != bound and int(self._d["info"][0].item()) != 0:
             # the reference's except-branch calls logging.ERROR(...) (stm.py:503-506) and dies
             raise np.linalg.LinAlgError("Cholesky Decomposition failed, because Sigma is not positive definite.")
-        return float(head[0])
+        return bound
 
     def _mstep_device(self):
         L, h, st = _lib.load(), self._ctx.handle, self._stream()
@@ -331,12 +362,12 @@ class STM:
             model = {"ridge": _lib.MODEL_STM_RIDGE, "lasso": _lib.MODEL_STM_LASSO}.get(self.mode, _lib.MODEL_STM)
         _lib.check(h, L.stm_mstep(h, self._ptr("stats"), self._ptr("x"), self._p, model, float(self.sigma_prior),
                                   self._ptr("gamma_t"), self._ptr("mu"), self._ptr("sigma"),
-                                  self._ptr("beta_t"), None, st))
+                                  self._ptr("beta_t"), self._ptr("beta64_t"), st))
         if self.model == "STM":
-            self.gamma = self._d["gamma_t"][:self._p].t().contiguous().cpu().numpy()  # K1 x p, stm.py:703
+            self._have_gamma = True     # K1 x p, stm.py:703 — fetched on access (no host sync in the EM loop)
         if not self.LDAbeta:
             self._update_kappa_device()
-        self._invalidate("mu", "sigma", "beta")
+        self._invalidate("mu", "sigma", "beta", "gamma")
 
     def _update_kappa_device(self):
         """update_beta with lda_beta=False -> mnreg (stm.py:746-853): kappa and beta from the reduced beta_ss."""
@@ -346,7 +377,7 @@ class STM:
             w = np.asarray(self.wcounts, dtype=np.float64)
             if self._presharded_total is not None:
                 t = torch.from_numpy(w.copy()).to(self._dev)
-                self._dist.all_reduce(t)
+                allreduce_stats(t, self._dist)
                 w = t.cpu().numpy()
             with np.errstate(divide="ignore"):
                 m = np.log(w) - np.log(np.sum(w))                      # stm.py:795-797
@@ -354,8 +385,12 @@ class STM:
             p_rows = self.K + self._nA + self._nA * self.K + 1
             self._d["kappa"] = torch.zeros((p_rows, self.V), dtype=torch.float64, device=self._dev)
         col = -1 if self.mnreg_column is None else int(self.mnreg_column)
+        if col < 0 and not getattr(self, "_warned_mnreg", False):
+            logger.warning("lda_beta=False: every word is regressed on its OWN count column (mnreg_column=None); the "
+                           "reference as written uses column 1 for every word (stm.py:825) - pass mnreg_column=1 for that")
+            self._warned_mnreg = True
         _lib.check(h, L.stm_update_kappa(h, self._ptr("stats"), self._ptr("logm"), 250.0, col, self._ptr("beta_t"),
-                                         None, self._ptr("kappa"), st))
+                                         self._ptr("beta64_t"), self._ptr("kappa"), st))
         self.kappa = self._d["kappa"].cpu().numpy()
 
     def E_step(self):
@@ -395,9 +430,7 @@ class STM:
         # moments of the current eta (E_step left them there; recompute in case eta was reassigned)
         L, h, st = _lib.load(), self._ctx.handle, self._stream()
         _lib.check(h, L.stm_moments(h, self._ptr("eta"), self._ptr("x"), self._p, self._ptr("stats"), st))
-        if self._dist is not None:
-            o4 = self._off[4]
-            self._dist.all_reduce(stats[o4:])
+        self._allreduce(stats[self._off[4]:])
         stats[self._off[3]] = float(self.N)
         self._mstep_device()
         torch.cuda.current_stream(self._dev).synchronize()
@@ -455,35 +488,68 @@ class STM:
     # ------------------------------------------------------------------------------------------------
     def eval_heldout(self, heldout, return_doc_ll=False):
         """Held-out likelihood of the fitted model by document completion (heldout.py:88-97; the evaluate step of
-        05_train.py:99-122) on the device-resident theta and beta: heldout[i] is scored with theta[i]."""
+        05_train.py:99-122) on the device-resident theta and the fp64 master beta: heldout[i] is scored with theta[i].
+
+        Document-sharded fits: `heldout` is indexed like the documents the constructor got (global indices, or the
+        local shard with presharded=True); every rank scores the held-out documents of ITS shard with its own theta
+        rows, and the mean is taken over all ranks (sum and count all-reduced).  All ranks must call it.  The
+        per-document values (return_doc_ll) are those of the local shard."""
         torch = self._torch
         if self._use_aspect:
             raise NotImplementedError("eval_heldout takes one K x V beta (no content covariate), heldout.py:88-97")
         ptr, ids, cnt = pack_corpus(list(heldout) if not isinstance(heldout, tuple) else heldout)
         D = ptr.shape[0] - 1
-        if D < 1 or D > self.N_local:
+        n_index = self.N_local if self._presharded_total is not None else self.N
+        if D < 1 or D > n_index:
             raise ValueError("held-out documents must be 1..N (document i is scored with theta[i])")
         if ids.size and (ids.min() < 0 or ids.max() >= self.V):
             raise IndexError("word id out of range [0, V)")
+        if self._dist is not None and self._presharded_total is None:
+            # global indexing: keep the documents of this rank's range [lo, hi); local row = i - lo
+            lo, hi = min(self._lo, D), min(self._hi, D)
+            ids, cnt = ids[ptr[lo]:ptr[hi]], cnt[ptr[lo]:ptr[hi]]
+            ptr = ptr[lo:hi + 1] - ptr[lo]
+            D = hi - lo
         dev = self._dev
-        d_ptr = torch.from_numpy(ptr).to(dev)
-        d_ids = torch.from_numpy(ids).to(dev) if ids.size else torch.zeros(1, dtype=torch.int32, device=dev)
-        d_cnt = torch.from_numpy(cnt).to(dev) if cnt.size else torch.zeros(1, dtype=torch.float32, device=dev)
-        out = torch.empty(D + 1, dtype=torch.float64, device=dev)
-        _lib.check(self._ctx.handle, _lib.load().stm_heldout(
-            self._ctx.handle, D, d_ptr.data_ptr(), d_ids.data_ptr(), d_cnt.data_ptr(), self._ptr("theta"),
-            self._ptr("beta_t"), out.data_ptr(), out.data_ptr() + 8 * D, self._stream()))
-        res = out.cpu().numpy()
-        return (float(res[D]), res[:D]) if return_doc_ll else float(res[D])
+        total = torch.zeros(2, dtype=torch.float64, device=dev)     # sum of per-document values, count
+        res = np.zeros(0)
+        if D >= 1:
+            d_ptr = torch.from_numpy(np.ascontiguousarray(ptr)).to(dev)
+            d_ids = torch.from_numpy(ids).to(dev) if ids.size else torch.zeros(1, dtype=torch.int32, device=dev)
+            d_cnt = torch.from_numpy(cnt).to(dev) if cnt.size else torch.zeros(1, dtype=torch.float32, device=dev)
+            out = torch.empty(D + 1, dtype=torch.float64, device=dev)
+            _lib.check(self._ctx.handle, _lib.load().stm_heldout64(
+                self._ctx.handle, D, d_ptr.data_ptr(), d_ids.data_ptr(), d_cnt.data_ptr(), self._ptr("theta"),
+                self._ptr("beta64_t"), out.data_ptr(), out.data_ptr() + 8 * D, self._stream()))
+            if self._dist is None:
+                res = out.cpu().numpy()
+                return (float(res[D]), res[:D]) if return_doc_ll else float(res[D])
+            total[0] = out[:D].sum()
+            total[1] = float(D)
+            res = out[:D].cpu().numpy()
+        allreduce_stats(total, self._dist)
+        mean = float((total[0] / total[1]).item())
+        return (mean, res) if return_doc_ll else mean
 
     def save_model(self, output_dir):
+        """stm.py:1120-1149, unchanged file formats.  Document-sharded fits: every rank takes part in the gathers
+        (theta / eta / mu are collectives), rank 0 alone writes the files; X is gathered when the ranks were given
+        their own shards (presharded)."""
+        beta, theta, sigma, eta, mu = self.beta, self.theta, self.sigma, self.eta, self.mu
+        X = self.X
+        if self._dist is not None and self._presharded_total is not None and X is not None:
+            parts = [None] * self.world
+            self._dist.all_gather_object(parts, np.asarray(X))
+            X = np.concatenate(parts, axis=0)
+        if self.rank != 0:
+            return
         os.makedirs(output_dir, exist_ok=True)
-        np.save(os.path.join(output_dir, "beta_hat"), self.beta)
-        np.save(os.path.join(output_dir, "theta_hat"), self.theta)
-        np.save(os.path.join(output_dir, "sigma_hat"), self.sigma)
-        np.save(os.path.join(output_dir, "eta_hat"), self.eta)
-        np.save(os.path.join(output_dir, "mu_hat"), self.mu)
-        np.save(os.path.join(output_dir, "X"), self.X)
+        np.save(os.path.join(output_dir, "beta_hat"), beta)
+        np.save(os.path.join(output_dir, "theta_hat"), theta)
+        np.save(os.path.join(output_dir, "sigma_hat"), sigma)
+        np.save(os.path.join(output_dir, "eta_hat"), eta)
+        np.save(os.path.join(output_dir, "mu_hat"), mu)
+        np.save(os.path.join(output_dir, "X"), X)
         if self.model == "STM":
             np.save(os.path.join(output_dir, "gamma_hat"), self.gamma)
         with open(os.path.join(output_dir, "lower_bound.pickle"), "wb") as f:

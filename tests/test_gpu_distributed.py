@@ -39,6 +39,21 @@ np.testing.assert_allclose(md.theta, ms.theta, atol=1e-4)            # gathered 
 np.testing.assert_allclose(md.beta, ms.beta, atol=1e-6)
 np.testing.assert_allclose(md.gamma, ms.gamma, atol=1e-5)
 np.testing.assert_allclose(md.sigma, ms.sigma, atol=1e-6)
+# held-out likelihood and persistence over sharded documents (ADVICE r01): global indexing, one mean, rank 0 writes
+held = docs
+hd, hs = md.eval_heldout(held), ms.eval_heldout(held)
+assert abs(hd - hs) <= 1e-6 * abs(hs), (hd, hs)
+out = os.path.join({tmp!r}, 'model')
+md.save_model(out)
+dist.barrier()
+assert np.load(os.path.join(out, 'theta_hat.npy')).shape == (md.N, K)
+assert np.load(os.path.join(out, 'X.npy')).shape[0] == md.N
+# every rank holds the same replicated model after the M-step
+for name in ('beta', 'sigma', 'gamma'):
+    t = torch.from_numpy(np.ascontiguousarray(getattr(md, name))).cuda()
+    lo_, hi_ = t.clone(), t.clone()
+    dist.all_reduce(lo_, op=dist.ReduceOp.MIN); dist.all_reduce(hi_, op=dist.ReduceOp.MAX)
+    assert torch.equal(lo_, hi_), name
 bss, sss = md.E_step(); md.M_step(bss, sss)
 bs2, ss2 = ms.E_step(); ms.M_step(bs2, ss2)
 np.testing.assert_allclose(bss, bs2, atol=1e-5); np.testing.assert_allclose(md.sigma, ms.sigma, atol=1e-6)
@@ -61,7 +76,7 @@ def test_two_gpu_em_matches_single_gpu(tmp_path):
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
     script = tmp_path / "worker.py"
-    script.write_text(_WORKER.format(root=ROOT))
+    script.write_text(_WORKER.format(root=ROOT, tmp=str(tmp_path)))
     with socket.socket() as s:
         s.bind(("127.0.0.1", 0))
         port = s.getsockname()[1]

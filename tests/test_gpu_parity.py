@@ -262,6 +262,53 @@ def test_front_estep_state_injection_matches_fixture():
     np.testing.assert_allclose(m.theta.sum(axis=1), 1.0, atol=1e-12)
 
 
+def test_front_host_views_are_read_only_and_beta_keeps_fp64():
+    """in-place edits of the host snapshots must not silently diverge from the device state, and beta keeps a
+    float64 master copy (assignment round-trips exactly; entries below the fp32 range do not flush to zero)."""
+    g = load_golden("estep_K5.npz")
+    K, V = int(g["K"]), int(g["V"])
+    m = _front(g, K, iters=2)
+    for name in ("eta", "mu", "theta", "sigma", "beta"):
+        with pytest.raises(ValueError):
+            getattr(m, name)[0, 0] = 1.0
+    b = np.random.default_rng(0).dirichlet(np.full(V, 0.05), K)
+    b[0, 0] = 1e-60                      # below the fp32 range
+    m.beta = b
+    np.testing.assert_array_equal(m.beta, b)
+    assert m.gamma is None
+    m.expectation_maximization(saving=False)
+    assert m.gamma.shape == (K - 1, 1)
+    bb = m.beta
+    assert bb.dtype == np.float64 and np.any(bb != bb.astype(np.float32))      # full fp64 precision, not an fp32 image
+    np.testing.assert_allclose(bb.sum(axis=1), 1.0, atol=1e-13)
+    # whole-attribute assignment reaches the device
+    e = np.array(m.eta) + 0.25
+    m.eta = e
+    np.testing.assert_array_equal(m.eta, e)
+
+
+def test_set_corpus_failure_keeps_the_previous_corpus(lib):
+    """stm_set_corpus validates everything before it releases the corpus that is loaded."""
+    g = load_golden("estep_K5.npz")
+    K, V = int(g["K"]), int(g["V"])
+    ctx = lib.Context(K, V, 1)
+    ctx.set_corpus(g["doc_ptr"], g["word_id"], g["count"])
+    pfx = "it0_"
+    args = (g[pfx + "beta"].astype(np.float64), g[pfx + "mu"], g[pfx + "siginv"], float(g[pfx + "sigmaentropy"]),
+            g[pfx + "eta0"])
+    b0 = ctx.estep_host(*args)["bound"]
+    big = lib.Context(K, 9000, 1)
+    with pytest.raises(lib.StmError):      # a document with more than 8192 distinct words
+        big.set_corpus(np.array([0, 8500]), np.arange(8500, dtype=np.int32), np.ones(8500, np.float32))
+    big.close()
+    with pytest.raises(lib.StmError):      # word id out of range: ctx keeps its corpus
+        ctx.set_corpus(np.array([0, 2]), np.array([0, V + 3], dtype=np.int32), np.ones(2, np.float32))
+    assert ctx.estep_host(*args)["bound"] == b0
+    import torch
+    assert torch.cuda.current_device() == 0
+    ctx.close()
+
+
 def test_content_front_mstep_keeps_reference_normalisation():
     g = load_golden("estep_content.npz")
     K, A = int(g["K"]), int(g["A"])
@@ -406,6 +453,34 @@ def test_em_trace_k50_spectral_vs_live_reference_and_c_oracle():
     assert rel[:7].max() < 1e-4, rel          # observed 3e-6
     assert rel.max() < 5e-3, rel              # observed 1.5e-3
     _teacher_forced(m, ref, (0, 1, 5, 10, 15, 20, len(ref["bounds"]) - 1), g["X"])
+
+
+def test_doc_bound_and_repair_vs_numpy_port_true_eigenvalues(lib):
+    """The per-document bound and the PD-repair stage of the CUDA path against the NumPy port, which tests positive
+    definiteness with np.linalg.eigvals like the reference (stm.py:1017) — not with the pivot shortcut the C oracle and
+    kernel B share — in K=50 spectral-init states where 100 % / ~45 % of the documents take the repair branch."""
+    g = load_golden("em_k50.npz")
+    K, V = int(g["K"]), int(g["V"])
+    ptr, ids, cnt = unpack_corpus(g)
+    nt = os.cpu_count() or 4
+    run = lambda *a, **k: c_oracle.estep(*a, nthreads=nt, **k)  # noqa: E731
+    ref = stm_numpy.em(ptr, ids, cnt, g["beta0"].astype(np.float64), g["X"], n_iter=2, estep_fn=run,
+                       round_beta32=True, keep_states=True)
+    sel = np.arange(0, len(ptr) - 1, 16)
+    ctx = lib.Context(K, V, 1)
+    ctx.set_corpus(ptr, ids, cnt)
+    for t in (0, 1):
+        st = ref["states"][t]
+        siginv, ent = stm_numpy.prologue(st["sigma"])
+        port = stm_numpy.estep(ptr, ids, cnt, st["beta"], st["mu"], siginv, ent, st["eta"], docs=sel)
+        o = ctx.estep_host(st["beta"], st["mu"], siginv, ent, st["eta"])
+        assert np.mean(port["repair"][sel] > 0) > 0.2
+        np.testing.assert_array_equal(o["repair"][sel], port["repair"][sel])
+        np.testing.assert_array_equal(o["status"][sel], port["status"][sel])
+        np.testing.assert_array_equal(o["nit"][sel], port["nit"][sel])
+        np.testing.assert_allclose(o["doc_bound"][sel], port["doc_bound"][sel], rtol=1e-9)
+        assert np.abs(o["eta"][sel] - port["eta"][sel]).max() < 1e-6
+    ctx.close()
 
 
 def test_em_trace_toy_ctm_vs_live_reference():

@@ -15,7 +15,8 @@ from oracle import c_oracle, stm_numpy
 from strutopy_b200 import _lib
 from strutopy_b200.corpus import pack_corpus, word_counts
 from oracle.stats_numpy import mstep_from_stats, pack_stats
-from strutopy_b200.parallel import shard_bounds, stats_layout
+from oracle.stats_numpy import stats_layout
+from strutopy_b200.parallel import shard_bounds
 from strutopy_b200.stm import design_matrix
 
 
@@ -137,7 +138,8 @@ import os, sys
 sys.path.insert(0, {root!r}); sys.path.insert(0, os.path.join({root!r}, 'tests'))
 import numpy as np, torch, torch.distributed as dist
 from conftest import load_golden
-from strutopy_b200.parallel import allreduce_stats, shard_bounds, stats_layout
+from oracle.stats_numpy import stats_layout
+from strutopy_b200.parallel import allreduce_stats, shard_bounds
 from oracle.stats_numpy import mstep_from_stats
 from test_host_logic import _shard_stats
 dist.init_process_group('gloo', rank=int(os.environ['RANK']), world_size=2)

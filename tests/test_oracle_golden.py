@@ -167,6 +167,32 @@ def test_em_k50_cut_trace_c_oracle():
     np.testing.assert_allclose(r["sigma"], g["cut_final_sigma"], atol=5e-2)
 
 
+def test_pd_test_by_pivots_equals_true_eigenvalues():
+    """The reference decides the Hessian repair with np.all(np.linalg.eigvals(H) > 0) (stm.py:1017); the C oracle (and
+    the CUDA kernel) decide it by the signs of the Cholesky pivots.  Pinned here against the NumPy port, which calls
+    np.linalg.eigvals exactly like the reference, on K=50 states where 100 % / ~45 % of the documents take the repair
+    branch: per-document repair stage EQUAL, per-document bound (whose log-determinant term depends on the repaired
+    matrix) <= 1e-9 relative."""
+    from conftest import unpack_corpus
+    g = load_golden("em_k50.npz")
+    ptr, ids, cnt = unpack_corpus(g)
+    run = lambda *a, **k: c_oracle.estep(*a, nthreads=4, **k)
+    ref = stm_numpy.em(ptr, ids, cnt, g["beta0"].astype(np.float64), g["X"], n_iter=2, estep_fn=run,
+                       round_beta32=True, keep_states=True)
+    sel = np.arange(0, len(ptr) - 1, 16)
+    for t, lo, hi in ((0, 0.99, 1.0), (1, 0.2, 0.8)):
+        st = ref["states"][t]
+        siginv, ent = stm_numpy.prologue(st["sigma"])
+        o = stm_numpy.estep(ptr, ids, cnt, st["beta"], st["mu"], siginv, ent, st["eta"], docs=sel)
+        c = c_oracle.estep(ptr, ids, cnt, st["beta"], st["mu"], siginv, ent, st["eta"], nthreads=4)
+        rate = float(np.mean(o["repair"][sel] > 0))
+        assert lo <= rate <= hi, rate
+        np.testing.assert_array_equal(c["repair"][sel], o["repair"][sel])
+        np.testing.assert_array_equal(c["status"][sel], o["status"][sel])
+        np.testing.assert_allclose(c["doc_bound"][sel], o["doc_bound"][sel], rtol=1e-9)
+        assert np.abs(c["eta"][sel] - o["eta"][sel]).max() < 1e-8
+
+
 def test_em_toy_ctm_trace_c_oracle():
     g = load_golden("em_toy_ctm.npz")
     run = lambda *a, **k: c_oracle.estep(*a, **k)
