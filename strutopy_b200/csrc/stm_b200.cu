@@ -30,6 +30,10 @@ struct LengthClass {
     int post_warps = 0, post_smem_per_warp = 0, post_grid = 0;
     int post_groups = 0;   // > 0: group version of kernel B, this many documents per CTA
     int post_gw = 3;       //      warps per document there
+    // host API (stm_estep_host): the class's documents split by document-index chunk, so that the copies of one
+    // chunk overlap the kernels of another; chunk_off[c] .. chunk_off[c+1] index d_chunk_docs
+    int* d_chunk_docs = nullptr;
+    std::vector<int> chunk_off;
 };
 
 }  // namespace
@@ -72,10 +76,17 @@ struct stm_ctx {
     cublasHandle_t cublas = nullptr;
     cusolverDnHandle_t cusolver = nullptr;
     int64_t launches = 0;
-    // stm_tune: cap on kernel A's warps per CTA
+    // stm_tune: cap on kernel A's warps per CTA; document chunks of the host API
     int tune_bfgs_max_warps = STM_BFGS_MAX_THREADS / 32;
+    int tune_host_chunks = 4;
     cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};   // E-step phases: before kernel A, between, after kernel B
-    cudaStream_t copy_stream = nullptr;                // host API: eta goes home while kernel B runs
+    // host API (stm_estep_host): compute stream, copy-in stream, copy-out stream; per-chunk events
+    // (inputs landed, kernel A done, kernel B done)
+    static constexpr int MAX_CHUNKS = 8;
+    int n_chunks = 1;
+    std::vector<int64_t> chunk_lo;                     // n_chunks + 1 document bounds
+    cudaStream_t host_stream = nullptr, in_stream = nullptr, copy_stream = nullptr;
+    cudaEvent_t ev_in[MAX_CHUNKS] = {}, ev_a[MAX_CHUNKS] = {}, ev_b[MAX_CHUNKS] = {}, ev_misc[2] = {};
     std::string err;
 };
 
@@ -534,7 +545,7 @@ void layout(const stm_ctx* c, int p, int64_t* off) {
 void free_corpus(stm_ctx* c) {
     cudaFree(c->d_doc_ptr); cudaFree(c->d_word_id); cudaFree(c->d_count); cudaFree(c->d_aspect);
     c->d_doc_ptr = nullptr; c->d_word_id = nullptr; c->d_count = nullptr; c->d_aspect = nullptr;
-    for (auto& lc : c->classes) cudaFree(lc.d_docs);
+    for (auto& lc : c->classes) { cudaFree(lc.d_docs); cudaFree(lc.d_chunk_docs); }
     c->classes.clear();
     cudaFree(c->d_queues); c->d_queues = nullptr;
     cudaFree(c->d_dbg); c->d_dbg = nullptr;
@@ -645,13 +656,19 @@ int stm_estep_kernel_ms(stm_ctx* ctx, double* ms2) {
 }
 
 // Tuning interface (explicit; the library reads no environment variables).  Takes effect at the next
-// stm_set_corpus.  Keys: "bfgs_max_warps" (cap on kernel A's warps = documents in flight per SM; occupancy studies).
+// stm_set_corpus.  Keys: "bfgs_max_warps" (cap on kernel A's warps = documents in flight per SM; occupancy studies),
+// "host_chunks" (1..8: document chunks whose copies stm_estep_host overlaps with the kernels of other chunks).
 int stm_tune(stm_ctx* ctx, const char* key, int value) {
     if (!ctx || !key) return STM_ERR_INVALID;
     const std::string k(key);
     if (k == "bfgs_max_warps") {
         if (value < 1) return fail(ctx, STM_ERR_INVALID, "bfgs_max_warps must be >= 1");
         ctx->tune_bfgs_max_warps = value;
+        return STM_OK;
+    }
+    if (k == "host_chunks") {
+        if (value < 1 || value > stm_ctx::MAX_CHUNKS) return fail(ctx, STM_ERR_INVALID, "host_chunks must be in 1..8");
+        ctx->tune_host_chunks = value;
         return STM_OK;
     }
     return fail(ctx, STM_ERR_INVALID, "stm_tune: unknown key " + k);
@@ -699,6 +716,14 @@ int stm_create(int device, int K, int V, int A, stm_ctx** out) {
     cudaMalloc(&c->d_potrf_work, sizeof(double) * c->potrf_lwork);
     for (int i = 0; i < 3; ++i) cudaEventCreate(&c->ev[i]);
     cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking);
+    cudaStreamCreateWithFlags(&c->host_stream, cudaStreamNonBlocking);
+    cudaStreamCreateWithFlags(&c->in_stream, cudaStreamNonBlocking);
+    for (int i = 0; i < stm_ctx::MAX_CHUNKS; ++i) {
+        cudaEventCreateWithFlags(&c->ev_in[i], cudaEventDisableTiming);
+        cudaEventCreateWithFlags(&c->ev_a[i], cudaEventDisableTiming);
+        cudaEventCreateWithFlags(&c->ev_b[i], cudaEventDisableTiming);
+    }
+    for (int i = 0; i < 2; ++i) cudaEventCreateWithFlags(&c->ev_misc[i], cudaEventDisableTiming);
     *out = c;
     return STM_OK;
 }
@@ -712,6 +737,14 @@ void stm_destroy(stm_ctx* c) {
     if (c->cusolver) cusolverDnDestroy(c->cusolver);
     for (int i = 0; i < 3; ++i) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
     if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
+    if (c->host_stream) cudaStreamDestroy(c->host_stream);
+    if (c->in_stream) cudaStreamDestroy(c->in_stream);
+    for (int i = 0; i < stm_ctx::MAX_CHUNKS; ++i) {
+        if (c->ev_in[i]) cudaEventDestroy(c->ev_in[i]);
+        if (c->ev_a[i]) cudaEventDestroy(c->ev_a[i]);
+        if (c->ev_b[i]) cudaEventDestroy(c->ev_b[i]);
+    }
+    for (int i = 0; i < 2; ++i) if (c->ev_misc[i]) cudaEventDestroy(c->ev_misc[i]);
     delete c;
 }
 
@@ -809,10 +842,25 @@ int stm_set_corpus(stm_ctx* ctx, int64_t D, const int64_t* doc_ptr, const int32_
     // everything is validated: release the previous corpus and take the new one
     free_corpus(ctx);
     ctx->D = D; ctx->nnz = nnz; ctx->n_max = n_max;
+    // host-API chunks: equal document ranges, enough documents per chunk to fill the GPU several times over
+    ctx->n_chunks = (int)std::max<int64_t>(1, std::min<int64_t>(ctx->tune_host_chunks, D / 8192));
+    ctx->chunk_lo.assign(ctx->n_chunks + 1, 0);
+    for (int c = 0; c <= ctx->n_chunks; ++c) ctx->chunk_lo[c] = D * c / ctx->n_chunks;
     for (size_t i = 0; i < new_classes.size(); ++i) {
         LengthClass& lc = new_classes[i];
         CU(cudaMalloc(&lc.d_docs, sizeof(int) * lc.n_docs));
         CU(cudaMemcpy(lc.d_docs, members[class_of[i]].data(), sizeof(int) * lc.n_docs, cudaMemcpyHostToDevice));
+        // the same documents grouped by chunk (each group keeps the longest-first order)
+        std::vector<int> grouped;
+        grouped.reserve(lc.n_docs);
+        lc.chunk_off.assign(1, 0);
+        for (int c = 0; c < ctx->n_chunks; ++c) {
+            for (int dd : members[class_of[i]])
+                if (dd >= ctx->chunk_lo[c] && dd < ctx->chunk_lo[c + 1]) grouped.push_back(dd);
+            lc.chunk_off.push_back((int)grouped.size());
+        }
+        CU(cudaMalloc(&lc.d_chunk_docs, sizeof(int) * lc.n_docs));
+        CU(cudaMemcpy(lc.d_chunk_docs, grouped.data(), sizeof(int) * lc.n_docs, cudaMemcpyHostToDevice));
         ctx->classes.push_back(lc);
     }
     CU(cudaMalloc(&ctx->d_doc_ptr, sizeof(long long) * (D + 1)));
@@ -827,7 +875,7 @@ int stm_set_corpus(stm_ctx* ctx, int64_t D, const int64_t* doc_ptr, const int32_
         CU(cudaMalloc(&ctx->d_aspect, sizeof(int) * std::max<int64_t>(D, 1)));
         CU(cudaMemcpy(ctx->d_aspect, aspect, sizeof(int) * D, cudaMemcpyHostToDevice));
     }
-    CU(cudaMalloc(&ctx->d_queues, sizeof(unsigned int) * 32));
+    CU(cudaMalloc(&ctx->d_queues, sizeof(unsigned int) * 32 * (stm_ctx::MAX_CHUNKS + 1)));
     CU(cudaMalloc(&ctx->d_dbg, sizeof(unsigned long long) * 16));
     CU(cudaMemset(ctx->d_dbg, 0, sizeof(unsigned long long) * 16));
     ctx->max_warps_total = std::max(max_warps, 1);
@@ -873,6 +921,79 @@ int stm_prologue(stm_ctx* ctx, const double* sigma_dev, double* prior_dev, int* 
     return STM_OK;
 }
 
+// device buffers of one E-step (what stm_estep is given)
+struct EstepBufs {
+    const float* beta_t; const double* mu; const double* prior;
+    double* eta; double* theta; double* stats; double* doc_bound; int32_t* doc_info; int32_t* doc_nfev;
+};
+
+// One phase (0: kernel A, per-document BFGS; 1: kernel B, post-optimisation) over every length class, for the whole
+// corpus (chunk < 0) or for the documents of one host-API chunk.
+static int launch_phase(stm_ctx* ctx, const EstepBufs& B, int phase, int chunk, cudaStream_t st) {
+    int64_t off[10];
+    layout(ctx, 0, off);
+    int ci = 0;
+    for (const auto& lc : ctx->classes) {
+        stm::EstepParams P;
+        P.doc_ptr = ctx->d_doc_ptr; P.word_id = ctx->d_word_id; P.count = ctx->d_count; P.aspect = ctx->d_aspect;
+        if (chunk < 0) { P.docs = lc.d_docs; P.n_docs = lc.n_docs; }
+        else { P.docs = lc.d_chunk_docs + lc.chunk_off[chunk]; P.n_docs = lc.chunk_off[chunk + 1] - lc.chunk_off[chunk]; }
+        P.queue = ctx->d_queues + 32 * (chunk + 1) + 16 * phase + ci;
+        ci++;
+        if (P.n_docs == 0) continue;
+        P.K = ctx->K; P.V = ctx->V; P.A = ctx->A; P.TS = ctx->TS;
+        P.beta_t = B.beta_t; P.mu = B.mu; P.prior = B.prior;
+        P.eta = B.eta; P.theta = B.theta; P.doc_bound = B.doc_bound; P.doc_info = B.doc_info;
+        P.doc_nfev = B.doc_nfev;
+        P.beta_ss_t = B.stats + off[0];
+        P.sigma_ss_rep = ctx->d_sigma_rep; P.n_rep = ctx->n_rep;
+        P.scratch = ctx->d_scratch; P.scratch_stride = ctx->scratch_stride;
+        P.n_cap = lc.n_cap; P.smem_per_warp = lc.smem_per_warp;
+        P.smem_small = lc.smem_small; P.tm_warps = lc.tm_warps; P.tm_cols = lc.tm_cols;
+        P.dbg_cycles = ctx->d_dbg;
+        if (phase == 0) {
+            const int grid = std::min(lc.grid, (P.n_docs + lc.warps - 1) / lc.warps);
+            CU(launch_bfgs(ctx->KPL, P, lc.J, grid, lc.warps * 32,
+                           (size_t)lc.smem_small * lc.warps + (size_t)lc.smem_per_warp * (lc.warps - lc.tm_warps), st));
+        } else {
+            P.smem_per_warp = lc.post_smem_per_warp;
+            if (lc.post_groups > 0) {
+                const size_t smem = (size_t)lc.post_smem_per_warp * lc.post_groups;
+                const int block = lc.post_groups * lc.post_gw * 32;
+                const int grid = std::min(lc.post_grid, (P.n_docs + lc.post_groups - 1) / lc.post_groups);
+                CU(ctx->KPL == 1   ? stm_launch_post_group_kpl1(P, lc.post_gw, grid, block, smem, st)
+                   : ctx->KPL == 2 ? stm_launch_post_group_kpl2(P, lc.post_gw, grid, block, smem, st)
+                   : ctx->KPL == 3 ? stm_launch_post_group_kpl3(P, lc.post_gw, grid, block, smem, st)
+                                   : stm_launch_post_group_kpl4(P, lc.post_gw, grid, block, smem, st));
+            } else {
+                const int grid = std::min(lc.post_grid, (P.n_docs + lc.post_warps - 1) / lc.post_warps);
+                CU(launch_post(ctx->KPL, P, grid, lc.post_warps * 32, (size_t)lc.post_smem_per_warp * lc.post_warps, st));
+            }
+        }
+        ctx->launches++;
+    }
+    return STM_OK;
+}
+
+static int estep_begin(stm_ctx* ctx, double* stats_dev, cudaStream_t st) {
+    int64_t off[10];
+    layout(ctx, 0, off);
+    CU(cudaMemsetAsync(stats_dev + off[0], 0, sizeof(double) * (size_t)ctx->A * ctx->V * ctx->TS, st));
+    CU(cudaMemsetAsync(ctx->d_sigma_rep, 0, sizeof(double) * ctx->n_rep * ctx->K1 * ctx->K1, st));
+    CU(cudaMemsetAsync(ctx->d_queues, 0, sizeof(unsigned int) * 32 * (stm_ctx::MAX_CHUNKS + 1), st));
+    return STM_OK;
+}
+
+static int estep_end(stm_ctx* ctx, const EstepBufs& B, cudaStream_t st) {
+    int64_t off[10];
+    layout(ctx, 0, off);
+    estep_epilogue_kernel<<<1, 1024, 0, st>>>(ctx->d_sigma_rep, ctx->n_rep, ctx->K1, B.doc_bound, ctx->D,
+                                              B.stats + off[1], B.stats + off[2], B.stats + off[3]);
+    ctx->launches++;
+    CU(cudaGetLastError());
+    return STM_OK;
+}
+
 int stm_estep(stm_ctx* ctx, const float* beta_t_dev, const double* mu_dev, const double* prior_dev,
               double* eta_dev, double* theta_dev, double* stats_dev, double* doc_bound_dev,
               int32_t* doc_info_dev, int32_t* doc_nfev_dev, void* stream) {
@@ -883,58 +1004,19 @@ int stm_estep(stm_ctx* ctx, const float* beta_t_dev, const double* mu_dev, const
         return fail(ctx, STM_ERR_INVALID, "NULL device pointer passed to stm_estep");
     cudaStream_t st = (cudaStream_t)stream;
     STM_ON_DEVICE(ctx);
-    int64_t off[10];
-    layout(ctx, 0, off);
-    const int K1 = ctx->K1;
-    CU(cudaMemsetAsync(stats_dev + off[0], 0, sizeof(double) * (size_t)ctx->A * ctx->V * ctx->TS, st));
-    CU(cudaMemsetAsync(ctx->d_sigma_rep, 0, sizeof(double) * ctx->n_rep * K1 * K1, st));
-    CU(cudaMemsetAsync(ctx->d_queues, 0, sizeof(unsigned int) * 32, st));
+    const EstepBufs B{beta_t_dev, mu_dev, prior_dev, eta_dev, theta_dev, stats_dev, doc_bound_dev, doc_info_dev,
+                      doc_nfev_dev};
+    int rc = estep_begin(ctx, stats_dev, st);
+    if (rc) return rc;
     // kernel A (BFGS) for every length class, then kernel B (post-optimisation) for every length class;
     // three events bracket the two phases (stm_estep_kernel_ms)
     CU(cudaEventRecord(ctx->ev[0], st));
     for (int phase = 0; phase < 2; ++phase) {
-        int ci = 0;
-        for (const auto& lc : ctx->classes) {
-            stm::EstepParams P;
-            P.doc_ptr = ctx->d_doc_ptr; P.word_id = ctx->d_word_id; P.count = ctx->d_count; P.aspect = ctx->d_aspect;
-            P.docs = lc.d_docs; P.n_docs = lc.n_docs; P.queue = ctx->d_queues + 16 * phase + ci;
-            P.K = ctx->K; P.V = ctx->V; P.A = ctx->A; P.TS = ctx->TS;
-            P.beta_t = beta_t_dev; P.mu = mu_dev; P.prior = prior_dev;
-            P.eta = eta_dev; P.theta = theta_dev; P.doc_bound = doc_bound_dev; P.doc_info = doc_info_dev;
-            P.doc_nfev = doc_nfev_dev;
-            P.beta_ss_t = stats_dev + off[0];
-            P.sigma_ss_rep = ctx->d_sigma_rep; P.n_rep = ctx->n_rep;
-            P.scratch = ctx->d_scratch; P.scratch_stride = ctx->scratch_stride;
-            P.n_cap = lc.n_cap; P.smem_per_warp = lc.smem_per_warp;
-            P.smem_small = lc.smem_small; P.tm_warps = lc.tm_warps; P.tm_cols = lc.tm_cols;
-            P.dbg_cycles = ctx->d_dbg;
-            if (phase == 0) {
-                CU(launch_bfgs(ctx->KPL, P, lc.J, lc.grid, lc.warps * 32,
-                               (size_t)lc.smem_small * lc.warps + (size_t)lc.smem_per_warp * (lc.warps - lc.tm_warps), st));
-            } else {
-                P.smem_per_warp = lc.post_smem_per_warp;
-                if (lc.post_groups > 0) {
-                    const size_t smem = (size_t)lc.post_smem_per_warp * lc.post_groups;
-                    const int block = lc.post_groups * lc.post_gw * 32;
-                    CU(ctx->KPL == 1   ? stm_launch_post_group_kpl1(P, lc.post_gw, lc.post_grid, block, smem, st)
-                       : ctx->KPL == 2 ? stm_launch_post_group_kpl2(P, lc.post_gw, lc.post_grid, block, smem, st)
-                       : ctx->KPL == 3 ? stm_launch_post_group_kpl3(P, lc.post_gw, lc.post_grid, block, smem, st)
-                                       : stm_launch_post_group_kpl4(P, lc.post_gw, lc.post_grid, block, smem, st));
-                } else {
-                    CU(launch_post(ctx->KPL, P, lc.post_grid, lc.post_warps * 32,
-                                   (size_t)lc.post_smem_per_warp * lc.post_warps, st));
-                }
-            }
-            ctx->launches++;
-            ci++;
-        }
+        rc = launch_phase(ctx, B, phase, -1, st);
+        if (rc) return rc;
         CU(cudaEventRecord(ctx->ev[phase + 1], st));
     }
-    estep_epilogue_kernel<<<1, 1024, 0, st>>>(ctx->d_sigma_rep, ctx->n_rep, K1, doc_bound_dev, ctx->D,
-                                              stats_dev + off[1], stats_dev + off[2], stats_dev + off[3]);
-    ctx->launches++;
-    CU(cudaGetLastError());
-    return STM_OK;
+    return estep_end(ctx, B, st);
 }
 
 int stm_moments(stm_ctx* ctx, const double* eta_dev, const double* x_dev, int p, double* stats_dev, void* stream) {
@@ -1117,46 +1199,73 @@ int stm_estep_host(stm_ctx* ctx, const double* beta, const double* mu, const dou
         CU(cudaMalloc(&ctx->h_doc_nfev, sizeof(int32_t) * std::max<int64_t>(D, 1)));
         ctx->host_bufs = true;
     }
-    cudaStream_t st = 0;
-    CU(cudaMemcpyAsync(ctx->h_beta_kv, beta, sizeof(double) * (size_t)A * K * V, cudaMemcpyHostToDevice, st));
-    CU(cudaMemcpyAsync(ctx->h_mu, mu, sizeof(double) * D * K1, cudaMemcpyHostToDevice, st));
-    CU(cudaMemcpyAsync(ctx->h_eta, eta, sizeof(double) * D * K1, cudaMemcpyHostToDevice, st));
-    CU(cudaMemcpyAsync(ctx->h_prior, prior.data(), sizeof(double) * (K1 + 1), cudaMemcpyHostToDevice, st));
+    // Three streams: inputs go up on `in`, the kernels run on `st`, results come home on `out`.  The documents are
+    // split into index chunks (stm_set_corpus); chunk c's mu / eta are copied while chunk c-1 computes, its eta goes
+    // home as soon as its kernel A is done and its theta / per-document outputs as soon as its kernel B is done.
+    cudaStream_t st = ctx->host_stream, in = ctx->in_stream, out = ctx->copy_stream;
+    const int NC = ctx->n_chunks;
+    CU(cudaMemcpyAsync(ctx->h_beta_kv, beta, sizeof(double) * (size_t)A * K * V, cudaMemcpyHostToDevice, in));
+    CU(cudaMemcpyAsync(ctx->h_prior, prior.data(), sizeof(double) * (K1 + 1), cudaMemcpyHostToDevice, in));
+    CU(cudaEventRecord(ctx->ev_misc[0], in));
+    for (int c = 0; c < NC; ++c) {
+        const int64_t lo = ctx->chunk_lo[c], n = ctx->chunk_lo[c + 1] - lo;
+        if (n > 0) {
+            CU(cudaMemcpyAsync(ctx->h_mu + lo * K1, mu + lo * K1, sizeof(double) * n * K1, cudaMemcpyHostToDevice, in));
+            CU(cudaMemcpyAsync(ctx->h_eta + lo * K1, eta + lo * K1, sizeof(double) * n * K1, cudaMemcpyHostToDevice, in));
+        }
+        CU(cudaEventRecord(ctx->ev_in[c], in));
+    }
+    CU(cudaStreamWaitEvent(st, ctx->ev_misc[0], 0));
     int rc = stm_beta_to_wordmajor(ctx, ctx->h_beta_kv, ctx->h_beta_t, st);
     if (rc) return rc;
-    rc = stm_estep(ctx, ctx->h_beta_t, ctx->h_mu, ctx->h_prior, ctx->h_eta, ctx->h_theta, ctx->h_stats,
-                   ctx->h_doc_bound, ctx->h_doc_info, ctx->h_doc_nfev, st);
+    const EstepBufs B{ctx->h_beta_t, ctx->h_mu, ctx->h_prior, ctx->h_eta, ctx->h_theta, ctx->h_stats, ctx->h_doc_bound,
+                      ctx->h_doc_info, ctx->h_doc_nfev};
+    rc = estep_begin(ctx, ctx->h_stats, st);
     if (rc) return rc;
-    // eta is final once kernel A is done (event ev[1]): copy it out on a second stream while kernel B runs
-    CU(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev[1], 0));
-    CU(cudaMemcpyAsync(eta, ctx->h_eta, sizeof(double) * D * K1, cudaMemcpyDeviceToHost, ctx->copy_stream));
-    rc = stm_wordmajor_to_kv(ctx, ctx->h_stats + off[0], ctx->h_bss_kv, st);
-    if (rc) return rc;
-    CU(cudaMemcpyAsync(theta, ctx->h_theta, sizeof(double) * D * K, cudaMemcpyDeviceToHost, st));
-    CU(cudaMemcpyAsync(beta_ss, ctx->h_bss_kv, sizeof(double) * (size_t)A * K * V, cudaMemcpyDeviceToHost, st));
-    CU(cudaMemcpyAsync(sigma_ss, ctx->h_stats + off[1], sizeof(double) * K1 * K1, cudaMemcpyDeviceToHost, st));
-    CU(cudaMemcpyAsync(bound, ctx->h_stats + off[2], sizeof(double), cudaMemcpyDeviceToHost, st));
-    if (doc_bound) CU(cudaMemcpyAsync(doc_bound, ctx->h_doc_bound, sizeof(double) * D, cudaMemcpyDeviceToHost, st));
-    if (doc_status || doc_nit || doc_repair) {
-        int32_t* u = ctx->h_doc_info;  // [3][D]: reuse the tail as unpack space (info itself is read first)
-        int32_t* st_d = u + D;         // status -> second third, nit/repair share: unpack per request
-        // unpack into two spare thirds, copying each requested field out
-        if (doc_status) {
-            unpack_info_kernel<<<256, 256, 0, st>>>(ctx->h_doc_info, D, st_d, nullptr, nullptr);
-            CU(cudaMemcpyAsync(doc_status, st_d, sizeof(int32_t) * D, cudaMemcpyDeviceToHost, st));
-        }
-        if (doc_nit) {
-            unpack_info_kernel<<<256, 256, 0, st>>>(ctx->h_doc_info, D, nullptr, u + 2 * D, nullptr);
-            CU(cudaMemcpyAsync(doc_nit, u + 2 * D, sizeof(int32_t) * D, cudaMemcpyDeviceToHost, st));
-        }
-        if (doc_repair) {
-            CU(cudaStreamSynchronize(st));
-            unpack_info_kernel<<<256, 256, 0, st>>>(ctx->h_doc_info, D, nullptr, nullptr, st_d);
-            CU(cudaMemcpyAsync(doc_repair, st_d, sizeof(int32_t) * D, cudaMemcpyDeviceToHost, st));
+    for (int c = 0; c < NC; ++c) {
+        const int64_t lo = ctx->chunk_lo[c], n = ctx->chunk_lo[c + 1] - lo;
+        CU(cudaStreamWaitEvent(st, ctx->ev_in[c], 0));
+        rc = launch_phase(ctx, B, 0, c, st);
+        if (rc) return rc;
+        CU(cudaEventRecord(ctx->ev_a[c], st));
+        rc = launch_phase(ctx, B, 1, c, st);
+        if (rc) return rc;
+        CU(cudaEventRecord(ctx->ev_b[c], st));
+        if (n > 0) {
+            CU(cudaStreamWaitEvent(out, ctx->ev_a[c], 0));
+            CU(cudaMemcpyAsync(eta + lo * K1, ctx->h_eta + lo * K1, sizeof(double) * n * K1, cudaMemcpyDeviceToHost, out));
+            CU(cudaStreamWaitEvent(out, ctx->ev_b[c], 0));
+            CU(cudaMemcpyAsync(theta + lo * K, ctx->h_theta + lo * K, sizeof(double) * n * K, cudaMemcpyDeviceToHost, out));
+            if (doc_bound)
+                CU(cudaMemcpyAsync(doc_bound + lo, ctx->h_doc_bound + lo, sizeof(double) * n, cudaMemcpyDeviceToHost, out));
         }
     }
+    rc = estep_end(ctx, B, st);
+    if (rc) return rc;
+    rc = stm_wordmajor_to_kv(ctx, ctx->h_stats + off[0], ctx->h_bss_kv, st);
+    if (rc) return rc;
+    // per-document diagnostics: unpacked on the compute stream into the two spare thirds of the info buffer
+    int32_t* u = ctx->h_doc_info;
+    if (doc_status) unpack_info_kernel<<<256, 256, 0, st>>>(ctx->h_doc_info, D, u + D, nullptr, nullptr);
+    if (doc_nit) unpack_info_kernel<<<256, 256, 0, st>>>(ctx->h_doc_info, D, nullptr, u + 2 * D, nullptr);
+    CU(cudaEventRecord(ctx->ev_misc[1], st));
+    CU(cudaStreamWaitEvent(out, ctx->ev_misc[1], 0));
+    CU(cudaMemcpyAsync(beta_ss, ctx->h_bss_kv, sizeof(double) * (size_t)A * K * V, cudaMemcpyDeviceToHost, out));
+    CU(cudaMemcpyAsync(sigma_ss, ctx->h_stats + off[1], sizeof(double) * K1 * K1, cudaMemcpyDeviceToHost, out));
+    CU(cudaMemcpyAsync(bound, ctx->h_stats + off[2], sizeof(double), cudaMemcpyDeviceToHost, out));
+    if (doc_status) CU(cudaMemcpyAsync(doc_status, u + D, sizeof(int32_t) * D, cudaMemcpyDeviceToHost, out));
+    if (doc_nit) CU(cudaMemcpyAsync(doc_nit, u + 2 * D, sizeof(int32_t) * D, cudaMemcpyDeviceToHost, out));
+    if (doc_repair) {
+        // reuses the status third: after the status copy (same stream order on `out`)
+        CU(cudaEventRecord(ctx->ev_misc[0], out));
+        CU(cudaStreamWaitEvent(st, ctx->ev_misc[0], 0));
+        unpack_info_kernel<<<256, 256, 0, st>>>(ctx->h_doc_info, D, nullptr, nullptr, u + D);
+        CU(cudaEventRecord(ctx->ev_misc[1], st));
+        CU(cudaStreamWaitEvent(out, ctx->ev_misc[1], 0));
+        CU(cudaMemcpyAsync(doc_repair, u + D, sizeof(int32_t) * D, cudaMemcpyDeviceToHost, out));
+    }
+    CU(cudaStreamSynchronize(out));
     CU(cudaStreamSynchronize(st));
-    CU(cudaStreamSynchronize(ctx->copy_stream));
     return STM_OK;
 }
 

@@ -18,6 +18,7 @@ import numpy as np
 
 from . import _lib
 from .corpus import pack_corpus
+from .parallel import allreduce_stats
 
 
 def keep_list(word_totals, maxV):
