@@ -156,7 +156,14 @@ def _ref_worker(args):
     from oracle import stm_numpy
     ptr, ids, cnt, beta, mu, siginv, ent, eta0, aspect = args
     t = time.perf_counter()
-    o = stm_numpy.estep(ptr, ids, cnt, beta, mu, siginv, ent, eta0, aspect=aspect)
+    try:
+        # one BLAS / LAPACK thread per worker process: the pool already uses every core (at K=100 a multi-threaded
+        # LAPACK in each of the workers oversubscribes the host 16x)
+        from threadpoolctl import threadpool_limits
+        with threadpool_limits(limits=1):
+            o = stm_numpy.estep(ptr, ids, cnt, beta, mu, siginv, ent, eta0, aspect=aspect)
+    except ImportError:
+        o = stm_numpy.estep(ptr, ids, cnt, beta, mu, siginv, ent, eta0, aspect=aspect)
     return time.perf_counter() - t, o["bound"], o["eta"], o["doc_bound"], o["repair"], o["status"], o["nit"]
 
 

@@ -169,9 +169,11 @@ int stm_heldout_host(stm_ctx* ctx, int64_t D, const int64_t* doc_ptr, const int3
  * needs ONE all-reduce (of gram_dev) between them:
  *   keep [n_keep]   HOST: the kept word ids in the reference's order, np.argsort(-wprob)[:maxV]
  *                   (stm.py:57; left to the caller so that ties break exactly as NumPy breaks them)
- *   gram_dev        DEVICE double [n_keep*n_keep + n_keep], caller-owned: this rank's part of
- *                   Htilde'Htilde (row-major upper triangle; stm.py:145-149) followed by diag(Hhat)
- *                   (stm.py:146).  stm_spectral_finish uses it as workspace (contents destroyed).
+ *   gram_dev        DEVICE double [n_keep*n_keep + n_keep], caller-owned.  After stm_spectral_gram: this rank's
+ *                   part of Htilde'Htilde (stm.py:145-149) as the PACKED row-major upper triangle in the first
+ *                   n_keep (n_keep + 1) / 2 entries (index of (i, j >= i): i n - i (i - 1) / 2 + j - i), and
+ *                   diag(Hhat) (stm.py:146) in the last n_keep entries — the two slices a document-sharded fit
+ *                   all-reduces.  stm_spectral_finish expands it in place and uses it as workspace.
  * stm_spectral_finish: Q = gram - Hhat and the row-sum assertion (stm.py:149-154; failing it returns
  * STM_ERR_INVALID with the reference's message), fastAnchor (stm.py:160-226), recover_l2
  * (stm.py:229-296; the per-word QP is solved exactly as NNLS), beta_new[:, keep] = beta, + 0.001/V,

@@ -56,32 +56,64 @@ __global__ void doc_scale_kernel(const long long* __restrict__ doc_ptr, const in
     }
 }
 
-// rows [d0, d0 + R) of Htilde = dtm / sqrt(divisor) (stm.py:145) as a dense, zero-initialised R x n block
-__global__ void densify_kernel(const long long* __restrict__ doc_ptr, const int* __restrict__ word_id,
-                               const float* __restrict__ count, const int* __restrict__ col_of,
-                               const double* __restrict__ div, long long d0, int R, int n, double* __restrict__ H) {
-    const int lane = threadIdx.x & 31;
-    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const int nwarps = (gridDim.x * blockDim.x) >> 5;
-    for (int r = warp; r < R; r += nwarps) {
-        const long long d = d0 + r, lo = doc_ptr[d], hi = doc_ptr[d + 1];
+// packed upper triangle (row-major, j >= i) of an n x n symmetric matrix
+__host__ __device__ inline size_t tri_index(int i, int j, int n) {
+    return (size_t)i * n - ((size_t)i * (i - 1)) / 2 + (size_t)(j - i);
+}
+__host__ __device__ inline size_t tri_size(int n) { return ((size_t)n * (n + 1)) / 2; }
+
+// Htilde'Htilde (stm.py:145-149) accumulated SPARSELY: one warp per document stages the document's kept entries
+// (column, count / sqrt(divisor)) in shared memory and adds the m (m + 1) / 2 products of its outer product into
+// the packed upper triangle with fp64 reductions (red.global.add.f64, resolved in L2: the 100 MB triangle at
+// maxV = 5000 mostly lives there).  Algorithmic work: sum_d m_d^2 / 2 multiply-adds (~0.7 G at BASELINE config 3)
+// instead of the 2.5e12 of the densify + Dsyrk version of round 1 (a library GEMM doing ~1000x the sparse work).
+__global__ void gram_outer_kernel(const long long* __restrict__ doc_ptr, const int* __restrict__ word_id,
+                                  const float* __restrict__ count, const int* __restrict__ col_of,
+                                  const double* __restrict__ div, long long D, int n, int cap,
+                                  double* __restrict__ tri) {
+    extern __shared__ __align__(16) unsigned char sm_raw[];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    double* hv = reinterpret_cast<double*>(sm_raw) + (size_t)w * cap;
+    int* hc = reinterpret_cast<int*>(reinterpret_cast<double*>(sm_raw) + (size_t)nw * cap) + (size_t)w * cap;
+    for (long long d = (long long)blockIdx.x * nw + w; d < D; d += (long long)gridDim.x * nw) {
+        const long long lo = doc_ptr[d], hi = doc_ptr[d + 1];
         const double s = sqrt(div[d]);
-        for (long long i = lo + lane; i < hi; i += 32) {
-            const int c = col_of[word_id[i]];
-            if (c >= 0) H[(size_t)r * n + c] = (double)count[i] / s;
+        // compact the kept entries (order within the document is irrelevant for a sum)
+        int m = 0;
+        for (long long i0 = lo; i0 < hi; i0 += 32) {
+            const long long i = i0 + lane;
+            const int c = (i < hi) ? col_of[word_id[i]] : -1;
+            const unsigned mask = __ballot_sync(0xffffffffu, c >= 0);
+            if (c >= 0) {
+                const int pos = m + __popc(mask & ((1u << lane) - 1u));
+                hc[pos] = c;
+                hv[pos] = (double)count[i] / s;
+            }
+            m += __popc(mask);
         }
+        __syncwarp();
+        for (int a = 0; a < m; ++a) {
+            const int ca = hc[a];
+            const double va = hv[a];
+            for (int b = lane; b <= a; b += 32) {
+                const int cb = hc[b];
+                const int i = min(ca, cb), j = max(ca, cb);
+                stm::red_add_f64(tri + tri_index(i, j, n), va * hv[b]);
+            }
+        }
+        __syncwarp();
     }
 }
 
-// Q = Htilde'Htilde - Hhat (stm.py:149): mirror the computed triangle, subtract the diagonal.
-// Dsyrk(LOWER) in cuBLAS's column-major view fills [i][j], j >= i of the row-major matrix.
-__global__ void symmetrise_kernel(double* __restrict__ Q, const double* __restrict__ hhat, int n) {
+// packed upper triangle -> full row-major matrix with the diagonal Hhat subtracted: Q = Htilde'Htilde - Hhat (stm.py:149)
+__global__ void expand_tri_kernel(const double* __restrict__ tri, const double* __restrict__ hhat, int n,
+                                  double* __restrict__ Q) {
     const long long total = (long long)n * n;
     for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total;
          t += (long long)gridDim.x * blockDim.x) {
         const int i = (int)(t / n), j = (int)(t % n);
-        if (j < i) Q[t] = Q[(size_t)j * n + i];
-        else if (j == i) Q[t] = Q[t] - hhat[i];
+        const double v = tri[(j >= i) ? tri_index(i, j, n) : tri_index(j, i, n)];
+        Q[t] = (i == j) ? v - hhat[i] : v;
     }
 }
 
@@ -493,10 +525,8 @@ int stm_spectral_gram(stm_ctx* ctx, int n_keep, const int32_t* keep, double* gra
         col_of[keep[i]] = i;
     }
     const int64_t D = ctx->D;
-    // dense chunk of documents: at most 512 MB
-    const int R = (int)std::max<int64_t>(1, std::min<int64_t>(std::max<int64_t>(D, 1), (512LL << 20) / (8LL * n)));
-    int* d_col = nullptr; double *d_div = nullptr, *d_H = nullptr; int* d_flag = nullptr;
-    auto cleanup = [&]() { cudaFree(d_col); cudaFree(d_div); cudaFree(d_H); cudaFree(d_flag); };
+    int* d_col = nullptr; double* d_div = nullptr; int* d_flag = nullptr;
+    auto cleanup = [&]() { cudaFree(d_col); cudaFree(d_div); cudaFree(d_flag); };
 #define SCU(call)                                                                                    \
     do {                                                                                             \
         cudaError_t e_ = (call);                                                                     \
@@ -507,7 +537,6 @@ int stm_spectral_gram(stm_ctx* ctx, int n_keep, const int32_t* keep, double* gra
     } while (0)
     SCU(cudaMalloc(&d_col, sizeof(int) * ctx->V));
     SCU(cudaMalloc(&d_div, sizeof(double) * std::max<int64_t>(D, 1)));
-    SCU(cudaMalloc(&d_H, sizeof(double) * (size_t)R * n));
     SCU(cudaMalloc(&d_flag, sizeof(int)));
     SCU(cudaMemcpyAsync(d_col, col_of.data(), sizeof(int) * ctx->V, cudaMemcpyHostToDevice, st));
     SCU(cudaMemsetAsync(d_flag, 0, sizeof(int), st));
@@ -516,22 +545,17 @@ int stm_spectral_gram(stm_ctx* ctx, int n_keep, const int32_t* keep, double* gra
     if (D > 0) {
         doc_scale_kernel<<<ctx->sm_count * 8, 256, 0, st>>>(ctx->d_doc_ptr, ctx->d_word_id, ctx->d_count, d_col, D,
                                                             d_div, hhat, d_flag);
-        ctx->launches++;
-    }
-    if (cublasSetStream(ctx->cublas, st) != CUBLAS_STATUS_SUCCESS) { cleanup(); return fail(ctx, STM_ERR_CUDA, "cublasSetStream"); }
-    const double one = 1.0;
-    for (int64_t d0 = 0; d0 < D; d0 += R) {
-        const int rows = (int)std::min<int64_t>(R, D - d0);
-        SCU(cudaMemsetAsync(d_H, 0, sizeof(double) * (size_t)rows * n, st));
-        densify_kernel<<<ctx->sm_count * 8, 256, 0, st>>>(ctx->d_doc_ptr, ctx->d_word_id, ctx->d_count, d_col, d_div,
-                                                          d0, rows, n, d_H);
-        ctx->launches++;
-        // row-major H (rows x n) is the column-major n x rows matrix A: gram += A A'
-        if (cublasDsyrk(ctx->cublas, CUBLAS_FILL_MODE_LOWER, CUBLAS_OP_N, n, rows, &one, d_H, n, &one, gram_dev, n) !=
-            CUBLAS_STATUS_SUCCESS) {
-            cleanup();
-            return fail(ctx, STM_ERR_CUDA, "cublasDsyrk failed");
-        }
+        // one warp per document; shared memory: 12 bytes per staged entry, capacity = the longest document
+        const int cap = (std::max(ctx->n_max, 1) + 1) & ~1;
+        int warps = (int)std::min<size_t>(8, (size_t)(ctx->max_smem - 1024) / ((size_t)cap * 12));
+        if (warps < 1) { cleanup(); return fail(ctx, STM_ERR_UNSUPPORTED, "stm_spectral_gram: document too long for the staging buffer"); }
+        const size_t smem = (size_t)warps * cap * 12;
+        SCU(cudaFuncSetAttribute(gram_outer_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        const int per_sm = std::max<int>(1, std::min<int>(8, (int)((size_t)ctx->max_smem / std::max<size_t>(smem, 1))));
+        gram_outer_kernel<<<ctx->sm_count * per_sm, warps * 32, smem, st>>>(ctx->d_doc_ptr, ctx->d_word_id, ctx->d_count,
+                                                                            d_col, d_div, (long long)D, n, cap, gram_dev);
+        ctx->launches += 2;
+        SCU(cudaGetLastError());
     }
     int flag = 0;
     SCU(cudaMemcpyAsync(&flag, d_flag, sizeof(int), cudaMemcpyDeviceToHost, st));
@@ -597,8 +621,11 @@ int stm_spectral_finish(stm_ctx* ctx, int n_keep, const int32_t* keep, const dou
     SCU(cudaMemcpyAsync(wprob, wprob_keep, sizeof(double) * n, cudaMemcpyHostToDevice, st));
 
     // ---- Q = Htilde'Htilde - Hhat, row-sum assertion (stm.py:149-154) ----
+    // gram_dev holds the packed upper triangle of Htilde'Htilde (what a sharded fit all-reduced) and diag(Hhat):
+    // expand it to the full matrix in place, through a copy of the triangle (fastAnchor's working buffer, not yet in use)
     double* Qc = gram_dev;   // becomes the caller's Q
-    symmetrise_kernel<<<ctx->sm_count * 8, 256, 0, st>>>(Qc, gram_dev + (size_t)n * n, n);
+    SCU(cudaMemcpyAsync(Q, gram_dev, sizeof(double) * tri_size(n), cudaMemcpyDeviceToDevice, st));   // Q: scratch until fastAnchor
+    expand_tri_kernel<<<ctx->sm_count * 8, 256, 0, st>>>(Q, gram_dev + (size_t)n * n, n, Qc);
     rowsum_check_kernel<<<ctx->sm_count * 8, 256, 0, st>>>(Qc, n, d_flag);
     ctx->launches += 2;
     int flag = 0;

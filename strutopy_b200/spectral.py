@@ -4,7 +4,7 @@ helpers `create_dtm` / `gram` / `fastAnchor` / `recover_l2` (stm.py:87-296).  SU
 Host side (this file, mirrors stm.py:51-59): word probabilities and the kept-word list
 `np.argsort(-wprob)[:maxV]` — the same NumPy call as the reference, so ties break identically.
 Device side (`stm_spectral_gram` / `stm_spectral_finish`, include/stm_b200.h): the Gram matrix
-Q = Htilde'Htilde - Hhat (cuBLAS Dsyrk over dense document chunks), the K anchor passes over Q, one
+Q = Htilde'Htilde - Hhat (sparse: one warp per document adds its outer product into the packed triangle), the K anchor passes over Q, one
 exact NNLS per word for recover_l2, and the K x V re-expansion.  With documents sharded over ranks the
 local Gram statistics are all-reduced ONCE between the two calls; everything after is replicated.
 
@@ -50,7 +50,9 @@ def spectral_on_context(ctx, torch, dev, word_totals, maxV=5000, dist=None, retu
         if int(bad.item()) and err is None:
             err = _lib.StmError(_lib.STM_ERR_INVALID, "Encountered zeroes in Q row sums, can not normalize. (another rank)")
         if err is None:
-            allreduce_stats(gram, dist)
+            # the packed upper triangle of Htilde'Htilde (n (n + 1) / 2 doubles: 100 MB at maxV = 5000) and diag(Hhat)
+            allreduce_stats(gram[:n * (n + 1) // 2], dist)
+            allreduce_stats(gram[n * n:], dist)
     if err is not None:
         _raise(err)
     beta = torch.empty((ctx.K, ctx.V), dtype=torch.float64, device=dev)
