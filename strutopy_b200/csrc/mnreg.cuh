@@ -92,6 +92,7 @@ __global__ void kappa_newton_kernel(const double* __restrict__ beta_ss_t, int A,
         };
 
         bool converged = false;
+        double gmax_last = INFINITY;
         for (int it = 0; it < 100 && !converged; ++it) {
             // mu, gradient
             double gmax = 0.0;
@@ -138,6 +139,7 @@ __global__ void kappa_newton_kernel(const double* __restrict__ beta_ss_t, int A,
                 b[r] = gt[k] + gaa + gi;
             }
             gmax = wmax(gmax);
+            gmax_last = gmax;
             if (!(gmax > gtol)) { converged = true; break; }
             __syncwarp();
             // (E + U U') zz = b :  tau_k, sigma_a, rhs
@@ -241,8 +243,12 @@ __global__ void kappa_newton_kernel(const double* __restrict__ beta_ss_t, int A,
             // backtracking (Armijo) on f
             const double f0 = objective(0.0, false);
             double s = 1.0;
-            bool ok = false;
-            for (int bt = 0; bt < 50; ++bt) {
+            // A Newton decrement below the resolution of f (n-term sums: ~1e-12 relative) cannot be tested through f:
+            // an Armijo test on rounding noise either rejects every step or accepts a tiny one and stalls (seen at
+            // 500k documents: 70 of 20 000 words took 100 noise-sized steps).  Newton's iteration converges
+            // quadratically there, so the full step is taken.
+            bool ok = (-slope <= 1e-10 * (1.0 + fabs(f0)));
+            for (int bt = 0; bt < 50 && !ok; ++bt) {
                 const double f1 = objective(s, true);
                 // Armijo, with the decrease allowed to drown in the rounding of f near the minimiser (so that
                 // full Newton steps keep being taken until the GRADIENT test above stops the iteration)
@@ -256,7 +262,9 @@ __global__ void kappa_newton_kernel(const double* __restrict__ beta_ss_t, int A,
             for (int a = 0; a < AMAX; ++a) av[a] += s * ga[a];
             __syncwarp();
         }
-        if (!converged && lane == 0) atomicExch(flag, 1);
+        // not converged to the 1e-12 target after 100 iterations is an error only if the gradient is not even 1000x below
+        // the 1e-5 at which the reference's solver (sklearn lbfgs, tol=1e-5) stops
+        if (!converged && !(gmax_last <= 1e-8 * (1.0 + ymax * inv_n)) && lane == 0) { atomicAdd(flag, 1); atomicExch(flag + 1, v); }
         // outputs: eta_r(v) for the softmax pass; kappa rows (stm.py:769-793 column layout: topics 0..K-1,
         // [K empty], aspects K+1..K+A, interactions K+A+1..K+A+n)
         for (int r = lane; r < n; r += 32) {
@@ -327,8 +335,8 @@ int stm_update_kappa(stm_ctx* ctx, const double* stats_dev, const double* logm_d
         }                                                                                            \
     } while (0)
     KCU(cudaMalloc(&lin, sizeof(double) * (size_t)n * V));
-    KCU(cudaMalloc(&d_flag, sizeof(int)));
-    KCU(cudaMemsetAsync(d_flag, 0, sizeof(int), st));
+    KCU(cudaMalloc(&d_flag, sizeof(int) * 2));
+    KCU(cudaMemsetAsync(d_flag, 0, sizeof(int) * 2, st));
     const size_t per_warp = sizeof(double) * (6 * (size_t)n + 4 * (size_t)K);
     int wpb = (int)std::min<size_t>(8, ((size_t)ctx->max_smem - 1024) / per_warp);
     if (wpb < 1) { cleanup(); return fail(ctx, STM_ERR_UNSUPPORTED, "stm_update_kappa: A*K too large for shared memory"); }
@@ -341,13 +349,27 @@ int stm_update_kappa(stm_ctx* ctx, const double* stats_dev, const double* logm_d
                                                       d_flag);
     kappa_softmax_kernel<<<n, 256, 0, st>>>(lin, logm_dev, A, K, V, TS, beta_t_dev, beta64_t_dev);
     ctx->launches += 2;
-    int flag = 0;
-    KCU(cudaMemcpyAsync(&flag, d_flag, sizeof(int), cudaMemcpyDeviceToHost, st));
+    int flag[2] = {0, 0};
+    KCU(cudaMemcpyAsync(flag, d_flag, sizeof(int) * 2, cudaMemcpyDeviceToHost, st));
     KCU(cudaStreamSynchronize(st));
     KCU(cudaGetLastError());
+    double ybad[4] = {0, 0, 0, 0};
+    if (flag[0]) {   // diagnostics of one word that failed: its largest / smallest count and whether any is not finite
+        std::vector<double> col((size_t)n);
+        const int vb = word_column >= 0 ? word_column : flag[1];
+        for (int r = 0; r < n; ++r)
+            cudaMemcpy(&col[r], stats_dev + off[0] + ((size_t)(r / K) * V + vb) * TS + (r % K), sizeof(double), cudaMemcpyDeviceToHost);
+        ybad[0] = *std::max_element(col.begin(), col.end());
+        ybad[1] = *std::min_element(col.begin(), col.end());
+        for (double c : col) if (!std::isfinite(c)) ybad[2] += 1.0;
+    }
 #undef KCU
     cleanup();
-    if (flag) return fail(ctx, STM_ERR_CUDA, "stm_update_kappa: Newton iteration did not converge for some word");
+    if (flag[0])
+        return fail(ctx, STM_ERR_CUDA, "stm_update_kappa: Newton iteration did not converge for " + std::to_string(flag[0]) +
+                                           " word(s), e.g. word " + std::to_string(flag[1]) + " (counts max " +
+                                           std::to_string(ybad[0]) + ", min " + std::to_string(ybad[1]) + ", non-finite " +
+                                           std::to_string((int)ybad[2]) + ")");
     return STM_OK;
 }
 
