@@ -1697,6 +1697,12 @@ constexpr int POST_GT = POST_GW * 32;
 __host__ __device__ constexpr int post_ust(int GW) {        // stride of the small fp64 vectors (Dg, u, d): >= 4 nb4
     return GW == 3 ? 56 : (GW == 5 ? 72 : (GW <= 11 ? 104 : 136));
 }
+#ifndef STM_ASM_BATCH
+#define STM_ASM_BATCH 1      // (r02 A/B at C3: 1 -> 8.44 ms, 4 -> 8.92 ms) Hessian elements per thread whose L2 loads are in flight together (kernel B assembly)
+#endif
+#ifndef STM_HESS_UNROLL
+#define STM_HESS_UNROLL 1    // unroll factor of the DMMA row pass over word quadruples
+#endif
 #ifndef STM_POST_MAX_THREADS
 #define STM_POST_MAX_THREADS 576        // 6 groups of 96 threads -> 112 registers per thread
 #endif
@@ -1734,7 +1740,7 @@ template <int NBMAX, int BR>
 __device__ __forceinline__ void hess_row_pass(const float* tile, int TS, int n, const double* wv, const double* wv2,
                                               const int* wid, const double (&ek)[NBMAX], double ekb, bool kok,
                                               double* ssb, int w4, int kk, double (&acc)[NBMAX][2], double& rs) {
-#pragma unroll 1
+STM_PRAGMA_(unroll STM_HESS_UNROLL)
     for (int vb = 0; vb < n; vb += 4) {
         const int v = vb + w4;
         const double sc = wv[v];                      // zero for the (< 4) slots past the last word
@@ -1999,18 +2005,38 @@ __global__ void __launch_bounds__(post_group_max_threads(GW), post_group_min_blo
         group_bar<GW>(grp);   // tile dead; Hg and v3 complete
 
         // ---- assemble H = data - N theta theta' + diag(-rowsum + N theta) + siginv (stm.py:1007-1015)
-        for (int r = wg; r < K1; r += POST_GW) {
-            const double thr = v2[r];
-            for (int k = lane; k <= r; k += 32) {
-                const double thk = v2[k];
-                double h = __ldcg(&Hg[(size_t)r * K1 + k]) - Nsum * (thr * thk);
-                if (k == r) {
-                    h = (h - v3[k] + Nsum * thk) + P.prior[k];
-                    Dg[k] = h;
-                    if (!(h > 0.0)) red[21] = 1.0;
+        // (the data term comes back from the L2 bounce: the loads of STM_ASM_BATCH elements are issued together so that
+        // one L2 round trip covers them — the element-at-a-time loop spent its time in long-scoreboard stalls)
+        {
+            const int ntri = K1 * (K1 + 1) / 2;
+            for (int base_i = 0; base_i < ntri; base_i += POST_GT * STM_ASM_BATCH) {
+                double hv[STM_ASM_BATCH];
+                int rr[STM_ASM_BATCH], kk_[STM_ASM_BATCH];
+#pragma unroll
+                for (int u = 0; u < STM_ASM_BATCH; ++u) {
+                    const int idx = base_i + u * POST_GT + gt;
+                    int r = (int)((sqrt(8.0 * (double)idx + 1.0) - 1.0) * 0.5);
+                    while ((r + 1) * (r + 2) / 2 <= idx) ++r;
+                    while (r * (r + 1) / 2 > idx) --r;
+                    rr[u] = r; kk_[u] = idx - r * (r + 1) / 2;
+                    hv[u] = (idx < ntri) ? __ldcg(&Hg[(size_t)r * K1 + kk_[u]]) : 0.0;
                 }
-                Hm[(size_t)r * HS + k] = h;
-                Hm[(size_t)k * HS + r] = h;
+#pragma unroll
+                for (int u = 0; u < STM_ASM_BATCH; ++u) {
+                    const int idx = base_i + u * POST_GT + gt;
+                    if (idx < ntri) {
+                        const int r = rr[u], k = kk_[u];
+                        const double thk = v2[k];
+                        double h = hv[u] - Nsum * (v2[r] * thk);
+                        if (k == r) {
+                            h = (h - v3[k] + Nsum * thk) + P.prior[k];
+                            Dg[k] = h;
+                            if (!(h > 0.0)) red[21] = 1.0;
+                        }
+                        Hm[(size_t)r * HS + k] = h;
+                        Hm[(size_t)k * HS + r] = h;
+                    }
+                }
             }
         }
         group_bar<GW>(grp);
