@@ -199,7 +199,9 @@ int stm_spectral_finish(stm_ctx* ctx, int n_keep, const int32_t* keep, const dou
  *   beta_t_dev   float [A][V][TS] out; beta64_t_dev double [A][V][TS] out or NULL
  *   kappa_dev    double [K+A+A*K+1][V] out or NULL (row K is the reference's empty column)
  * The minimiser is unique (strictly convex); it is computed by damped Newton to ~1e-12, sklearn's lbfgs
- * stops at a 1e-5 gradient: agreement ~1e-8.  A >= 2, A <= 8.  Blocks until done. */
+ * stops at a 1e-5 gradient: agreement ~1e-8.  A >= 2, A <= 8.  Blocks until done.  * kappa_dev, when it is the buffer the previous successful call on this context wrote (same word_column),
+ * seeds the Newton iteration: the problem is strictly convex, so the minimiser is the same; it is reached in 1-3
+ * steps instead of 5-9. */
 int stm_update_kappa(stm_ctx* ctx, const double* stats_dev, const double* logm_dev, double alpha,
                      int word_column, float* beta_t_dev, double* beta64_t_dev, double* kappa_dev, void* stream);
 

@@ -79,6 +79,10 @@ struct stm_ctx {
     // stm_tune: cap on kernel A's warps per CTA; document chunks of the host API
     int tune_bfgs_max_warps = STM_BFGS_MAX_THREADS / 32;
     int tune_host_chunks = 4;
+    double* d_kappa_lin = nullptr;        // stm_update_kappa workspace
+    int64_t kappa_lin_len = 0;
+    const double* kappa_warm = nullptr;   // stm_update_kappa: coefficient buffer of the last successful call (warm start)
+    int kappa_warm_column = -2;
     cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};   // E-step phases: before kernel A, between, after kernel B
     // host API (stm_estep_host): compute stream, copy-in stream, copy-out stream; per-chunk events
     // (inputs landed, kernel A done, kernel B done)
@@ -733,6 +737,7 @@ void stm_destroy(stm_ctx* c) {
     DeviceGuard guard(c->device);
     free_corpus(c);
     cudaFree(c->d_msmall); cudaFree(c->d_info); cudaFree(c->d_potrf_work); cudaFree(c->d_syevd_work);
+    cudaFree(c->d_kappa_lin);
     if (c->cublas) cublasDestroy(c->cublas);
     if (c->cusolver) cusolverDnDestroy(c->cusolver);
     for (int i = 0; i < 3; ++i) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
@@ -841,6 +846,7 @@ int stm_set_corpus(stm_ctx* ctx, int64_t D, const int64_t* doc_ptr, const int32_
     }
     // everything is validated: release the previous corpus and take the new one
     free_corpus(ctx);
+    ctx->kappa_warm = nullptr;
     ctx->D = D; ctx->nnz = nnz; ctx->n_max = n_max;
     // host-API chunks: equal document ranges, enough documents per chunk to fill the GPU several times over
     ctx->n_chunks = (int)std::max<int64_t>(1, std::min<int64_t>(ctx->tune_host_chunks, D / 8192));

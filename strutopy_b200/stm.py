@@ -96,7 +96,6 @@ class STM:
         if self.A == 1:
             logging.warning("no dimension for the topical content provided")
         self.mnreg_column = mnreg_column
-        self.kappa = None
         if not self.LDAbeta and not (self.interactions and self.A and int(self.A) >= 2):
             raise NotImplementedError(
                 "lda_beta=False (STM.mnreg, stm.py:749-853) is the CONTENT model: it needs kappa_interactions=True, "
@@ -232,6 +231,15 @@ class STM:
             self._ctx.handle, src.data_ptr(), self._ptr("beta_t"), self._stream()))
         torch.cuda.current_stream(self._dev).synchronize()
         self._invalidate("beta")
+
+    @property
+    def kappa(self):
+        """content-covariate coefficients (stm.py:841), p x V; None before the first update (fetched on access)"""
+        if "kappa" not in self._d:
+            return None
+        if "kappa" not in self._host:
+            self._host["kappa"] = self._ro(self._d["kappa"].cpu().numpy())
+        return self._host["kappa"]
 
     @property
     def gamma(self):
@@ -391,7 +399,7 @@ class STM:
             self._warned_mnreg = True
         _lib.check(h, L.stm_update_kappa(h, self._ptr("stats"), self._ptr("logm"), 250.0, col, self._ptr("beta_t"),
                                          self._ptr("beta64_t"), self._ptr("kappa"), st))
-        self.kappa = self._d["kappa"].cpu().numpy()
+        self._invalidate("kappa")
 
     def E_step(self):
         """stm.py:489-597 — returns (beta_ss, sigma_ss) as host arrays in the reference's layout."""
