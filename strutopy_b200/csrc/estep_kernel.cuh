@@ -1779,6 +1779,38 @@ struct HessDispatch<NBMAX, -1> {
                                                double (&)[NBMAX][2], double&) {}
 };
 
+// K > 64 (more than 8 block rows): the Hessian data term is cut into WORK UNITS (row block br, NC <= 7 consecutive
+// column blocks from c0) instead of whole row blocks.  A unit needs 2 NC accumulators and NC exponentials instead of
+// 2 (br + 1) and 16 (the 11- and 17-warp instantiations spilled ~1 KB per thread), and 19 units of <= 7 block pairs
+// deal over 11 warps with a maximum of 9 pairs per warp where whole row blocks gave 13 (K = 100).  Static NC, run-time
+// br / c0: 7 instantiations instead of one per block row.
+template <int NC>
+__device__ __forceinline__ void hess_unit_pass(const float* tile, int TS, int n, const double* wv, const double* wv2,
+                                               const int* wid, const double (&ek)[7], double ekb, bool kok, double* ssb,
+                                               int w4, int kk, int br, int c0, bool do_phi, double (&acc)[7][2],
+                                               double& rs) {
+#pragma unroll 1
+    for (int vb = 0; vb < n; vb += 4) {
+        const int v = vb + w4;
+        const double sc = wv[v];                      // zero for the (< 4) slots past the last word
+        const float* tb = tile + (size_t)min(v, n - 1) * TS + kk;
+        double fr[NC];
+#pragma unroll
+        for (int t = 0; t < NC; ++t) fr[t] = (beta_f2d(tb[8 * (c0 + t)]) * ek[t]) * sc;
+        const double fa = (beta_f2d(tb[8 * br]) * ekb) * sc;
+        if (do_phi && v < n && kok) {
+            const double ph = fa * wv2[v];
+            rs += ph;
+            if (!STM_DBG_NO_PHI) red_add_f64(ssb + (size_t)wid[v] * TS, ph);
+        }
+#pragma unroll
+        for (int t = 0; t < NC; ++t)
+            asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                         : "+d"(acc[t][0]), "+d"(acc[t][1])
+                         : "d"(fa), "d"(fr[t]));
+    }
+}
+
 template <int KPL, int GW>
 __global__ void __launch_bounds__(post_group_max_threads(GW), post_group_min_blocks(GW)) post_group_kernel(const EstepParams P) {
     constexpr int POST_GW = GW, POST_GT = GW * 32, POST_UST = post_ust(GW);
@@ -1826,6 +1858,23 @@ __global__ void __launch_bounds__(post_group_max_threads(GW), post_group_min_blo
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     group_bar<GW>(grp);
     uint32_t parity = 0;
+    // K > 64: Hessian work units (block row, <= 7 consecutive column blocks), largest first (see hess_unit_pass)
+    __shared__ unsigned short units_s[64];
+    __shared__ int unit_count_s;
+    if constexpr (NBMAX > 8) {
+        if (threadIdx.x == 0) {
+            const int nbp_ = (K + 7) >> 3;
+            int cnt = 0;
+            for (int sz = 7; sz >= 1; --sz)
+                for (int br = nbp_ - 1; br >= 0; --br)
+                    for (int j = 0; 7 * j <= br; ++j) {
+                        const int nc = (br + 1 - 7 * j) < 7 ? (br + 1 - 7 * j) : 7;
+                        if (nc == sz) units_s[cnt++] = (unsigned short)(br | (j << 4) | (nc << 8));
+                    }
+            unit_count_s = cnt;
+        }
+        __syncthreads();
+    }
 
     const int ggrp = blockIdx.x * (blockDim.x / POST_GT) + grp;
     double* Hg = P.scratch + (size_t)ggrp * P.scratch_stride + (size_t)K1 * K1;   // Hessian bounce (L2)
@@ -1954,6 +2003,52 @@ __global__ void __launch_bounds__(post_group_max_threads(GW), post_group_min_blo
             double ek[NBMAX];   // exp(eta~) of this lane's topics (zero beyond K)
 #pragma unroll
             for (int t = 0; t < NBMAX; ++t) ek[t] = v0[8 * t + kk];
+            if constexpr (NBMAX > 8) {
+                // the unit table (built once per CTA, below the kernel prologue): descending size, dealt in snake order
+                const int nunits = unit_count_s;
+                int slot = 0;
+#pragma unroll 1
+                for (int u = 0; u < nunits; ++u, ++slot) {
+                    const int m6 = slot % (2 * POST_GW);
+                    if ((m6 < POST_GW ? m6 : 2 * POST_GW - 1 - m6) != wg) continue;
+                    const int code = __reduce_max_sync(STM_FULL, (int)units_s[u]);   // provably uniform
+                    const int br = code & 15, c0 = 7 * ((code >> 4) & 3), nc = (code >> 8) & 7;
+                    double acc[7][2], ek7[7];
+#pragma unroll
+                    for (int t = 0; t < 7; ++t) { acc[t][0] = 0.0; acc[t][1] = 0.0; ek7[t] = (t < nc) ? v0[8 * (c0 + t) + kk] : 0.0; }
+                    double rs = 0.0;
+                    const int kb = 8 * br + kk;
+                    const double ekb = v0[kb];
+                    const bool kok = kb < K;
+                    const bool do_phi = (c0 == 0);
+                    double* ssb = beta_ss_a + kb;
+                    switch (nc) {
+                        case 1: hess_unit_pass<1>(tile, TS, n, wv, wv2, wid, ek7, ekb, kok, ssb, w4, kk, br, c0, do_phi, acc, rs); break;
+                        case 2: hess_unit_pass<2>(tile, TS, n, wv, wv2, wid, ek7, ekb, kok, ssb, w4, kk, br, c0, do_phi, acc, rs); break;
+                        case 3: hess_unit_pass<3>(tile, TS, n, wv, wv2, wid, ek7, ekb, kok, ssb, w4, kk, br, c0, do_phi, acc, rs); break;
+                        case 4: hess_unit_pass<4>(tile, TS, n, wv, wv2, wid, ek7, ekb, kok, ssb, w4, kk, br, c0, do_phi, acc, rs); break;
+                        case 5: hess_unit_pass<5>(tile, TS, n, wv, wv2, wid, ek7, ekb, kok, ssb, w4, kk, br, c0, do_phi, acc, rs); break;
+                        case 6: hess_unit_pass<6>(tile, TS, n, wv, wv2, wid, ek7, ekb, kok, ssb, w4, kk, br, c0, do_phi, acc, rs); break;
+                        default: hess_unit_pass<7>(tile, TS, n, wv, wv2, wid, ek7, ekb, kok, ssb, w4, kk, br, c0, do_phi, acc, rs); break;
+                    }
+                    const int gi = br * 8 + kk;
+#pragma unroll
+                    for (int t = 0; t < 7; ++t) {
+                        if (t < nc) {
+#pragma unroll
+                            for (int c = 0; c < 2; ++c) {
+                                const int gj = (c0 + t) * 8 + 2 * w4 + c;
+                                if (gi < K1 && gj <= gi) Hg[(size_t)gi * K1 + gj] = acc[t][c];
+                            }
+                        }
+                    }
+                    if (do_phi) {
+                        rs += __shfl_xor_sync(STM_FULL, rs, 1);
+                        rs += __shfl_xor_sync(STM_FULL, rs, 2);
+                        if (w4 == 0 && kb < KV) v3[kb] = rs;
+                    }
+                }
+            } else {
             int qpos = 0;
 #pragma unroll 1
             for (int br = nbp - 1; br >= 0; --br, ++qpos) {
@@ -2002,6 +2097,7 @@ __global__ void __launch_bounds__(post_group_max_threads(GW), post_group_min_blo
                 if (w4 == 0 && kb < KV) v3[kb] = rs;
             }
         }
+            }
         group_bar<GW>(grp);   // tile dead; Hg and v3 complete
 
         // ---- assemble H = data - N theta theta' + diag(-rowsum + N theta) + siginv (stm.py:1007-1015)
