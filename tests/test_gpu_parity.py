@@ -309,6 +309,36 @@ def test_set_corpus_failure_keeps_the_previous_corpus(lib):
     ctx.close()
 
 
+def test_host_call_chunking_is_transparent(lib):
+    """stm_estep_host overlaps copies and kernels over document chunks (stm_tune host_chunks): per-document results do
+    not depend on the chunking (bit for bit), the statistics only through the order of their fp64 reductions."""
+    K, V, D = 8, 400, 40000
+    rng = np.random.default_rng(7)
+    n = rng.integers(5, 25, size=D)
+    ptr = np.zeros(D + 1, np.int64)
+    np.cumsum(n, out=ptr[1:])
+    ids = np.concatenate([np.sort(rng.choice(V, size=k, replace=False)) for k in n]).astype(np.int32)
+    cnt = rng.integers(1, 4, size=int(ptr[-1])).astype(np.float64)
+    beta = rng.dirichlet(np.full(V, 0.1), K)
+    mu = rng.normal(0, 0.3, size=(D, K - 1))
+    eta0 = rng.normal(0, 0.3, size=(D, K - 1))
+    siginv, ent = c_oracle.prologue(np.eye(K - 1) * 2.0)
+    outs = []
+    for chunks in (1, 4):
+        ctx = lib.Context(K, V, 1, tune={"host_chunks": chunks})
+        ctx.set_corpus(ptr, ids, cnt)
+        outs.append(ctx.estep_host(beta, mu, siginv, ent, eta0))
+        ctx.close()
+    a, b = outs
+    for k in ("eta", "theta", "doc_bound", "status", "nit", "repair"):
+        np.testing.assert_array_equal(a[k], b[k])
+    assert a["bound"] == b["bound"]
+    np.testing.assert_allclose(a["beta_ss"], b["beta_ss"], rtol=1e-12, atol=1e-12)
+    np.testing.assert_allclose(a["sigma_ss"], b["sigma_ss"], rtol=1e-12)
+    with pytest.raises(lib.StmError):
+        lib.Context(K, V, 1, tune={"no_such_key": 1})
+
+
 def test_content_front_mstep_keeps_reference_normalisation():
     g = load_golden("estep_content.npz")
     K, A = int(g["K"]), int(g["A"])
