@@ -379,6 +379,8 @@ def ours(args):
     import torch
     import torch.distributed as dist
     from strutopy_b200 import STM, _lib
+    if args.tune:
+        _lib.DEFAULT_TUNE = {kv.split("=")[0]: int(kv.split("=")[1]) for kv in args.tune.split(",")}
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -648,6 +650,7 @@ def main():
     ap.add_argument("--ref-docs-per-core", type=int, default=48)
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline / parity legs")
     ap.add_argument("--no-strong", action="store_true", help="N > 1: skip the strong-scaling block")
+    ap.add_argument("--tune", default="", help="stm_tune overrides for every context, e.g. host_chunks=8 (A/B runs)")
     args = ap.parse_args()
     if args.impl == "reference":
         reference_arm(args)

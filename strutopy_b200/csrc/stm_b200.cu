@@ -78,7 +78,7 @@ struct stm_ctx {
     int64_t launches = 0;
     // stm_tune: cap on kernel A's warps per CTA; document chunks of the host API
     int tune_bfgs_max_warps = STM_BFGS_MAX_THREADS / 32;
-    int tune_host_chunks = 4;
+    int tune_host_chunks = 3;   // r02 A/B at C3, N=1: e2e / value 0.971 (1 chunk), 1.005 (3), 0.999 (4), 0.989 (5)
     double* d_kappa_lin = nullptr;        // stm_update_kappa workspace
     int64_t kappa_lin_len = 0;
     const double* kappa_warm = nullptr;   // stm_update_kappa: coefficient buffer of the last successful call (warm start)
@@ -851,7 +851,15 @@ int stm_set_corpus(stm_ctx* ctx, int64_t D, const int64_t* doc_ptr, const int32_
     // host-API chunks: equal document ranges, enough documents per chunk to fill the GPU several times over
     ctx->n_chunks = (int)std::max<int64_t>(1, std::min<int64_t>(ctx->tune_host_chunks, D / 8192));
     ctx->chunk_lo.assign(ctx->n_chunks + 1, 0);
-    for (int c = 0; c <= ctx->n_chunks; ++c) ctx->chunk_lo[c] = D * c / ctx->n_chunks;
+    if (ctx->n_chunks >= 3) {
+        // small first and last chunks (their copies are the ones nothing overlaps), the rest split evenly
+        const int64_t edge = (int64_t)((double)D / (2.5 * ctx->n_chunks));
+        const int mid = ctx->n_chunks - 2;
+        for (int c = 1; c < ctx->n_chunks; ++c) ctx->chunk_lo[c] = edge + (D - 2 * edge) * (c - 1) / mid;
+        ctx->chunk_lo[ctx->n_chunks] = D;
+    } else {
+        for (int c = 0; c <= ctx->n_chunks; ++c) ctx->chunk_lo[c] = D * c / ctx->n_chunks;
+    }
     for (size_t i = 0; i < new_classes.size(); ++i) {
         LengthClass& lc = new_classes[i];
         CU(cudaMalloc(&lc.d_docs, sizeof(int) * lc.n_docs));
