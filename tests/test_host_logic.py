@@ -229,15 +229,20 @@ def test_bench_reference_arm_contract():
     """`bench.py --impl reference` (the reference's CPU path = the NumPy/SciPy port on host cores) runs without a GPU
     and prints one JSON line with the keys the driver reads."""
     import json
+    # a small shape, so that the whole arm (one warm-up EM iteration of the C oracle, the process pool, the one-core
+    # figure) runs in seconds; the host-side spectral init it uses at full size is pinned in tests/test_spectral.py
     out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1",
-                          "--warmup", "0", "--ref-docs-per-core", "1"], capture_output=True, text=True, timeout=300)
+                          "--warmup", "1", "--ref-docs-per-core", "1", "--docs", "3000", "--K", "20", "--V", "3000", "--init", "random"],
+                         capture_output=True, text=True, timeout=300)
     assert out.returncode == 0, out.stderr[-2000:]
     line = json.loads(out.stdout.strip().splitlines()[-1])
     assert line["impl"] == "reference" and line["metric"] == "estep_docs_per_sec_K50_V10k" and line["unit"] == "docs/s"
     assert line["higher_is_better"] is True and line["value"] > 0 and line["steps"] == 1
     assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
     assert line["e2e"] == {"value": line["value"], "unit": "docs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
-    assert "workload" in line["config"]
+    assert "workload" in line["config"] and line["config"]["init"] == "random"
+    assert line["cpu_baseline"]["one_core_as_shipped"]["cores"] == 1
+    assert "same state" in line["cpu_baseline"]["sample"]
 
 
 def test_matrix_market_corpus_round_trip(tmp_path):

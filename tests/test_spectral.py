@@ -40,6 +40,20 @@ def test_oracle_stages_vs_live_reference(tag):
     np.testing.assert_allclose(beta.sum(axis=1), 1.0 / K, rtol=1e-9)   # total-sum normalisation, stm.py:82
 
 
+@pytest.mark.parametrize("tag", ["t", "f"])
+def test_oracle_fast_path_vs_live_reference(tag):
+    """spectral_init_fast (sparse Gram + compiled NNLS: what bench.py's reference arm prepares the benchmark state
+    with at D=100k, where the dense document-term matrix does not fit) against the live reference's fixture."""
+    g = load_golden("spectral.npz")
+    ptr, ids, cnt, K, V, maxV = _case(g, tag)
+    keep = sn.keep_order(sn.word_prob(ptr, ids, cnt), maxV)
+    np.testing.assert_allclose(sn.gram_sparse(ptr, ids, cnt, keep), g[tag + "_Q"], rtol=1e-11, atol=1e-14)
+    beta, anchors, _ = sn.spectral_init_fast(ptr, ids, cnt, K, V, maxV)
+    ref = g[tag + "_beta"]
+    np.testing.assert_array_equal(anchors, keep[g[tag + "_anchor"]])
+    assert np.abs(beta - ref).max() <= 1e-8 * ref.max()
+
+
 def test_oracle_wiki_vs_live_reference():
     g, w = load_golden("spectral.npz"), load_golden("wiki_corpus.npz")
     K = int(g["w_cfg"][2])
