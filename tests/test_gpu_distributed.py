@@ -1,4 +1,7 @@
-"""2-GPU data-parallel EM (NCCL) against the single-GPU run: skipped when fewer than 2 GPUs."""
+"""Data-parallel EM over two ranks against the single-process run: NCCL on two GPUs when the box has them; on a
+one-GPU box the SAME test runs with both ranks on cuda:0 and the gloo backend (which all-reduces CUDA tensors through
+the host), so that the sharded path — nnz-balanced shards, the one all-reduce per iteration, the replicated M-step,
+sharded spectral init, eval_heldout, save_model — is exercised wherever the GPU tests run."""
 import os
 import socket
 import subprocess
@@ -17,13 +20,19 @@ sys.path.insert(0, {root!r}); sys.path.insert(0, os.path.join({root!r}, 'tests')
 import numpy as np, torch, torch.distributed as dist
 from conftest import load_golden
 from strutopy_b200 import STM
-rank = int(os.environ['RANK']); torch.cuda.set_device(rank)
-dist.init_process_group('nccl', device_id=torch.device('cuda', rank))
+rank = int(os.environ['RANK'])
+two = torch.cuda.device_count() >= 2
+dev_index = rank if two else 0
+torch.cuda.set_device(dev_index)
+if two:
+    dist.init_process_group('nccl', device_id=torch.device('cuda', dev_index))
+else:
+    dist.init_process_group('gloo')
 g = load_golden('em_c1.npz'); K, V = int(g['K']), int(g['V'])
 docs = (g['doc_ptr'], g['word_id'], g['count'])
 def fit(distributed):
     m = STM(docs, range(V), False, K, g['X'], False, 6, 0, 0.0, init_type='random', model_type='STM',
-            device=rank, distributed=distributed)
+            device=dev_index, distributed=distributed)
     m.beta = g['beta0']
     m.expectation_maximization(saving=False)
     return m
@@ -62,8 +71,8 @@ sp = load_golden('spectral.npz')
 sdocs = (sp['f_doc_ptr'], sp['f_word_id'], sp['f_count'].astype(np.float64))
 Ks, Vs = int(sp['f_cfg'][2]), sp['f_beta'].shape[1]
 Xs = (np.arange(len(sdocs[0]) - 1) % 2).astype(np.float64)[:, None]
-bd = STM(sdocs, range(Vs), False, Ks, Xs, False, 2, 0, 0.0, init_type='spectral', device=rank, distributed=True).beta
-b1 = STM(sdocs, range(Vs), False, Ks, Xs, False, 2, 0, 0.0, init_type='spectral', device=rank, distributed=False).beta
+bd = STM(sdocs, range(Vs), False, Ks, Xs, False, 2, 0, 0.0, init_type='spectral', device=dev_index, distributed=True).beta
+b1 = STM(sdocs, range(Vs), False, Ks, Xs, False, 2, 0, 0.0, init_type='spectral', device=dev_index, distributed=False).beta
 assert np.abs(bd - b1).max() <= 2e-7 * b1.max(), np.abs(bd - b1).max()   # beta is stored in fp32
 assert np.abs(bd - sp['f_beta']).max() <= 2e-7 * sp['f_beta'].max()
 dist.barrier(); dist.destroy_process_group()
@@ -73,8 +82,7 @@ print('rank', rank, 'ok')
 
 def test_two_gpu_em_matches_single_gpu(tmp_path):
     import torch
-    if torch.cuda.device_count() < 2:
-        pytest.skip("needs 2 GPUs")
+    assert torch.cuda.is_available()
     script = tmp_path / "worker.py"
     script.write_text(_WORKER.format(root=ROOT, tmp=str(tmp_path)))
     with socket.socket() as s:
