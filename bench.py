@@ -622,7 +622,10 @@ def ours(args):
             "cpu_baseline": cpu,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "api": "stm_estep_host (C ABI, fp64 host buffers in the reference's layouts; corpus resident; "
-                           "documents chunked so that copies overlap kernels)"},
+                           "documents chunked so that copies overlap kernels)",
+                    "state": f"every call runs the E-step of the snapshot state (EM iteration {args.warmup}); `value` "
+                             f"averages the EM iterations {args.warmup}..{args.warmup + args.steps - 1}, whose E-steps "
+                             "differ in cost by a few percent"},
             "gpu_launches": int(launches), "clocks": clocks,
             "elbo_trace_tail": bounds[-3:], "parity": parity, "strong": strong,
         }
