@@ -279,6 +279,9 @@ def reference_arm(args):
               f"the CUDA arm's first timed E-step ({args.init} init + {args.warmup} EM iterations, prepared on the host in "
               f"{t_prep:.0f} s, untimed); NumPy/SciPy E-step (oracle/stm_numpy.py == reference arithmetic) in {nproc} "
               f"processes forked before the timed region")
+    if A > 1:
+        sample += ("; config 5: the reference's own kappa update (mnreg) cannot run (SURVEY 8a), so the host-side warm-up "
+                   "iterations use its LDA-style update_beta — the E-step timed is the same function on a state of the same kind")
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * wall / args.steps,
