@@ -779,6 +779,11 @@ __global__ void __launch_bounds__(STM_BFGS_MAX_THREADS, 1) bfgs_kernel(const Est
         const int maxiter = K1 * 200;
         double alpha = 0.0, f_eval = 0.0, dphi = 0.0;
         int have_cache = 0, have_cache2 = 0;
+        // phi'(alpha) = g . p of the two memoised points: what SciPy's memoised gradient gives back for a repeated
+        // trial point is the SAME value as the first time, so the value of the fresh evaluation is kept (and the
+        // memo-hit path no longer runs a reduction); invalid after the direction p has changed
+        double dphi2 = 0.0;
+        int dphi_ok = 0, dphi2_ok = 0;
         if (STM_LS_REGS || lane == 0) {
             S.old_fval = 0.0; S.old_old_fval = 0.0; S.gnorm = 0.0; S.derphi0 = 0.0; S.f2 = 0.0;
             S.brackt = 0; S.stage = 1; S.w1_it = 0; S.w2_i = 0; S.z_i = 0;
@@ -813,12 +818,15 @@ __global__ void __launch_bounds__(STM_BFGS_MAX_THREADS, 1) bfgs_kernel(const Est
                         const double tg = gt[i]; gt[i] = gt2[i]; gt2[i] = tg;
                     }
                     const double tf = f_eval; f_eval = S.f2; S.f2 = tf;
+                    const double td = dphi; dphi = dphi2; dphi2 = td;
+                    const int tk = dphi_ok; dphi_ok = dphi2_ok; dphi2_ok = tk;
                     have_cache2 = have_cache;  // both valid after a swap
                 }
                 if (!hit0 && !hit1) {
 #pragma unroll
                     for (int i = 0; i < KPL; ++i) { xt2[i] = xt[i]; gt2[i] = gt[i]; }
                     S.f2 = f_eval;
+                    dphi2 = dphi; dphi2_ok = dphi_ok;
                     have_cache2 = have_cache;
                     nfev++;
                     have_cache = 1;
@@ -972,13 +980,15 @@ __global__ void __launch_bounds__(STM_BFGS_MAX_THREADS, 1) bfgs_kernel(const Est
                         gt[i] = (k < K1) ? (Sd[i] * dk - (a[i] - scale * ex[i])) : 0.0;
                     }
                     dphi = red[4] + scale * red[5];   // = gt . p
+                    dphi_ok = 1;
                     STM_T(t_e6);
                     STM_TACC(13, t_e5, t_e6);       // slot 13: lse + f + gradient
-                } else {
+                } else if (!dphi_ok) {
                     double dp_l2 = 0.0;
 #pragma unroll
                     for (int i = 0; i < KPL; ++i) dp_l2 += gt[i] * p[i];
                     dphi = warp_sum(dp_l2);
+                    dphi_ok = 1;
                 }
             }
 
@@ -1244,6 +1254,7 @@ __global__ void __launch_bounds__(STM_BFGS_MAX_THREADS, 1) bfgs_kernel(const Est
 #pragma unroll
                         for (int i = 0; i < KPL; ++i) p[i] = -g[i];  // Hk = I
                     }
+                    dphi_ok = 0; dphi2_ok = 0;   // new direction: the memoised g . p are stale
                     double d_l = 0.0;
 #pragma unroll
                     for (int i = 0; i < KPL; ++i) d_l += g[i] * p[i];
