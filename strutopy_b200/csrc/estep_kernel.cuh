@@ -1709,7 +1709,7 @@ __host__ __device__ constexpr int post_ust(int GW) {        // stride of the sma
     return GW == 3 ? 56 : (GW == 5 ? 72 : (GW <= 11 ? 104 : 136));
 }
 #ifndef STM_ASM_BATCH
-#define STM_ASM_BATCH 1      // (r02 A/B at C3: 1 -> 8.44 ms, 4 -> 8.92 ms) Hessian elements per thread whose L2 loads are in flight together (kernel B assembly)
+#define STM_ASM_BATCH 2      // (r02 A/B at C3 with stepped indices: 1 / 2 / 4 -> 8.34 / 8.32 / 8.37 ms) Hessian elements per thread whose L2 loads are in flight together (kernel B assembly)
 #endif
 #ifndef STM_HESS_UNROLL
 #define STM_HESS_UNROLL 1    // unroll factor of the DMMA row pass over word quadruples
@@ -2112,36 +2112,36 @@ __global__ void __launch_bounds__(post_group_max_threads(GW), post_group_min_blo
         group_bar<GW>(grp);   // tile dead; Hg and v3 complete
 
         // ---- assemble H = data - N theta theta' + diag(-rowsum + N theta) + siginv (stm.py:1007-1015)
-        // (the data term comes back from the L2 bounce: the loads of STM_ASM_BATCH elements are issued together so that
-        // one L2 round trip covers them — the element-at-a-time loop spent its time in long-scoreboard stalls)
+        // (the data term comes back from the L2 bounce.  The threads walk the packed lower triangle, element gt, gt + GT,
+        // ...: (row, column) is stepped forward by GT elements per visit — no square root per element — and the loads
+        // of STM_ASM_BATCH visits are issued together so that one L2 round trip covers them)
         {
             const int ntri = K1 * (K1 + 1) / 2;
-            for (int base_i = 0; base_i < ntri; base_i += POST_GT * STM_ASM_BATCH) {
+            int r = 0, k = gt;                       // element gt of the packed triangle = (r, k)
+            while (k > r) { k -= r + 1; ++r; }
+            for (int base_i = gt; base_i < ntri; base_i += POST_GT * STM_ASM_BATCH) {
                 double hv[STM_ASM_BATCH];
                 int rr[STM_ASM_BATCH], kk_[STM_ASM_BATCH];
 #pragma unroll
                 for (int u = 0; u < STM_ASM_BATCH; ++u) {
-                    const int idx = base_i + u * POST_GT + gt;
-                    int r = (int)((sqrt(8.0 * (double)idx + 1.0) - 1.0) * 0.5);
-                    while ((r + 1) * (r + 2) / 2 <= idx) ++r;
-                    while (r * (r + 1) / 2 > idx) --r;
-                    rr[u] = r; kk_[u] = idx - r * (r + 1) / 2;
-                    hv[u] = (idx < ntri) ? __ldcg(&Hg[(size_t)r * K1 + kk_[u]]) : 0.0;
+                    rr[u] = r; kk_[u] = k;
+                    hv[u] = (base_i + u * POST_GT < ntri) ? __ldcg(&Hg[(size_t)r * K1 + k]) : 0.0;
+                    k += POST_GT;
+                    while (k > r) { k -= r + 1; ++r; }
                 }
 #pragma unroll
                 for (int u = 0; u < STM_ASM_BATCH; ++u) {
-                    const int idx = base_i + u * POST_GT + gt;
-                    if (idx < ntri) {
-                        const int r = rr[u], k = kk_[u];
-                        const double thk = v2[k];
-                        double h = hv[u] - Nsum * (v2[r] * thk);
-                        if (k == r) {
-                            h = (h - v3[k] + Nsum * thk) + P.prior[k];
-                            Dg[k] = h;
+                    if (base_i + u * POST_GT < ntri) {
+                        const int r_ = rr[u], k_ = kk_[u];
+                        const double thk = v2[k_];
+                        double h = hv[u] - Nsum * (v2[r_] * thk);
+                        if (k_ == r_) {
+                            h = (h - v3[k_] + Nsum * thk) + P.prior[k_];
+                            Dg[k_] = h;
                             if (!(h > 0.0)) red[21] = 1.0;
                         }
-                        Hm[(size_t)r * HS + k] = h;
-                        Hm[(size_t)k * HS + r] = h;
+                        Hm[(size_t)r_ * HS + k_] = h;
+                        Hm[(size_t)k_ * HS + r_] = h;
                     }
                 }
             }
