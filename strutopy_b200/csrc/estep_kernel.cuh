@@ -1763,7 +1763,7 @@ STM_PRAGMA_(unroll STM_HESS_UNROLL)
         if (v < n && kok) {
             const double ph = fa * wv2[v];
             rs += ph;
-            if (!STM_DBG_NO_PHI) red_add_f64(ssb + (size_t)wid[v] * TS, ph);
+            if (!STM_DBG_NO_PHI) red_add_f64(ssb + wid[v], ph);
         }
 #pragma unroll
         for (int t = 0; t <= BR; ++t)
@@ -1812,7 +1812,7 @@ __device__ __forceinline__ void hess_unit_pass(const float* tile, int TS, int n,
         if (do_phi && v < n && kok) {
             const double ph = fa * wv2[v];
             rs += ph;
-            if (!STM_DBG_NO_PHI) red_add_f64(ssb + (size_t)wid[v] * TS, ph);
+            if (!STM_DBG_NO_PHI) red_add_f64(ssb + wid[v], ph);
         }
 #pragma unroll
         for (int t = 0; t < NC; ++t)
@@ -1926,7 +1926,7 @@ __global__ void __launch_bounds__(post_group_max_threads(GW), post_group_min_blo
         for (int v = gt; v < n; v += POST_GT) {
             const int w = P.word_id[p0 + v];
             const float c = P.count[p0 + v];
-            wid[v] = w;
+            wid[v] = w * TS;   // row offset into beta_ss (V * TS < 2^31), so that the phi scatter needs no 64-bit multiply
             cw[v] = c;
             nsum_l += (double)c;
             tma_row_g2s(tile + (size_t)v * TS, beta_a + (size_t)w * TS, (uint32_t)(TS * 4), mbar);
