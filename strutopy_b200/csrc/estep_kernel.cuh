@@ -1756,12 +1756,15 @@ STM_PRAGMA_(unroll STM_HESS_UNROLL)
         const int v = vb + w4;
         const double sc = wv[v];                      // zero for the (< 4) slots past the last word
         const float* tb = tile + (size_t)min(v, n - 1) * TS + kk;
+        // sum_v b_v b_v' with b = beta e sqrt(c) / colsum = (beta e) sc: the word's scale goes into the A fragment as
+        // sc^2, so that a B fragment costs one multiplication instead of two
         double fr[BR + 1];
 #pragma unroll
-        for (int t = 0; t <= BR; ++t) fr[t] = (beta_f2d(tb[8 * t]) * ek[t]) * sc;
-        const double fa = (beta_f2d(tb[8 * BR]) * ekb) * sc;   // == fr[BR] bit for bit
+        for (int t = 0; t <= BR; ++t) fr[t] = beta_f2d(tb[8 * t]) * ek[t];
+        const double be = beta_f2d(tb[8 * BR]) * ekb;
+        const double fa = be * (sc * sc);
         if (v < n && kok) {
-            const double ph = fa * wv2[v];
+            const double ph = be * (sc * wv2[v]);
             rs += ph;
             if (!STM_DBG_NO_PHI) red_add_f64(ssb + wid[v], ph);
         }
@@ -1807,10 +1810,11 @@ __device__ __forceinline__ void hess_unit_pass(const float* tile, int TS, int n,
         const float* tb = tile + (size_t)min(v, n - 1) * TS + kk;
         double fr[NC];
 #pragma unroll
-        for (int t = 0; t < NC; ++t) fr[t] = (beta_f2d(tb[8 * (c0 + t)]) * ek[t]) * sc;
-        const double fa = (beta_f2d(tb[8 * br]) * ekb) * sc;
+        for (int t = 0; t < NC; ++t) fr[t] = beta_f2d(tb[8 * (c0 + t)]) * ek[t];
+        const double be = beta_f2d(tb[8 * br]) * ekb;
+        const double fa = be * (sc * sc);              // the word's scale enters once, squared, on the A side
         if (do_phi && v < n && kok) {
-            const double ph = fa * wv2[v];
+            const double ph = be * (sc * wv2[v]);
             rs += ph;
             if (!STM_DBG_NO_PHI) red_add_f64(ssb + wid[v], ph);
         }
