@@ -65,6 +65,9 @@
 #define STM_DBG_SKIP_DENSE 0
 #endif
 #ifndef STM_BFGS_MAX_THREADS
+#ifndef STM_W1_TAIL_SKIP
+#define STM_W1_TAIL_SKIP 1    // 1: leave a DCSRCH search whose bracket has collapsed onto memoised points that can never be accepted
+#endif                        //    (exact: see the comment at the use; r02: kernel A 28.4 -> ... ms)
 #define STM_BFGS_MAX_THREADS 384   // launch bound of kernel A (register budget = 65536 / this): 12 warps x 160 registers, no spills (r01 A/B: 448 -> 384: 31.3 -> 29.3 ms)
 #endif
 #define STM_PRAGMA2_(x) _Pragma(#x)
@@ -796,6 +799,7 @@ __global__ void __launch_bounds__(STM_BFGS_MAX_THREADS, 1) bfgs_kernel(const Est
         while (!done) {
             // ---------------- evaluate f, g at x + alpha p --------------------------------------
             STM_T(t_ev0);
+            bool memo_hit = false;
             {
                 double xn[KPL];
                 bool same0 = have_cache, same1 = have_cache2;
@@ -811,6 +815,7 @@ __global__ void __launch_bounds__(STM_BFGS_MAX_THREADS, 1) bfgs_kernel(const Est
                 // a collapsing dcsrch interval (~20 % of all evaluations).
                 const bool hit0 = __all_sync(STM_FULL, same0);
                 const bool hit1 = !hit0 && __all_sync(STM_FULL, same1);
+                memo_hit = hit0 || hit1;
                 if (hit1) {
 #pragma unroll
                     for (int i = 0; i < KPL; ++i) {
@@ -1080,7 +1085,47 @@ __global__ void __launch_bounds__(STM_BFGS_MAX_THREADS, 1) bfgs_kernel(const Est
                         (S.brackt && S.stmax - S.stmin <= xtol * S.stmax))
                         stp = S.stx;
                     S.w1_it++;
-                    if (!isfinite(stp) || S.w1_it >= 100) start_w2 = 1;  // WARN / maxiter -> stp None
+                    bool dead = false;
+#if STM_W1_TAIL_SKIP
+                    // The tail of a failing search.  Near convergence the steps are so small against x that the
+                    // whole bracket [stmin, stmax] maps onto one or two neighbouring trial vectors x + stp p, both
+                    // memoised, and DCSRCH spends its remaining (up to 100) iterations alternating between them
+                    // until xtol or maxiter ends it with stp = None (-> Wolfe-2).  That outcome is known as soon as
+                    //  (1) the vectors at the two ends of the bracket differ in at most ONE component: every later
+                    //      trial lies in the bracket (_dcsrch.py:472-500 keeps stp in [stmin, stmax], the bracket only
+                    //      shrinks) and fl(x_i + fl(stp p_i)) is monotone in stp, so every later trial vector is one
+                    //      of those two;
+                    //  (2) both are memoised with their phi and phi', and neither can pass the convergence test
+                    //      (_dcsrch.py:373: f <= finit + stp gtest and |g| <= gtol |ginit|) for ANY stp of the bracket:
+                    //      |phi'| fails, or phi is above the test line at stmin (gtest < 0: the line only falls).
+                    // No further evaluation would be fresh, no trial accepted, and nothing of the DCSRCH state
+                    // outlives the search: going to Wolfe-2 now is what the replay arrives at.  On the C oracle
+                    // (D=3000 of the C3 workload) this removes 64 % of the memo-hit steps and never fires before an
+                    // acceptance (0 of 2593 searches).
+                    if (memo_hit && S.brackt && have_cache2 && dphi_ok && dphi2_ok) {
+                        bool a0 = true, a1 = true, b0 = true, b1 = true;
+                        int nd_l = 0;
+#pragma unroll
+                        for (int i = 0; i < KPL; ++i) {
+                            const double xa = __dadd_rn(x[i], __dmul_rn(S.stmin, p[i]));
+                            const double xb = __dadd_rn(x[i], __dmul_rn(S.stmax, p[i]));
+                            a0 = a0 && (xa == xt[i]); a1 = a1 && (xa == xt2[i]);
+                            b0 = b0 && (xb == xt[i]); b1 = b1 && (xb == xt2[i]);
+                            nd_l += !(xa == xb);
+                        }
+                        const bool A0 = __all_sync(STM_FULL, a0), A1 = __all_sync(STM_FULL, a1);
+                        const bool B0 = __all_sync(STM_FULL, b0), B1 = __all_sync(STM_FULL, b1);
+                        const int nd = __reduce_add_sync(STM_FULL, nd_l);
+                        if (nd <= 1 && (A0 || A1) && (B0 || B1)) {
+                            const double top = S.finit + S.stmin * S.gtest, gmax = c2 * -S.ginit;
+                            const bool never0 = !(fabs(dphi) <= gmax) || !(f_eval <= top);
+                            const bool never1 = !(fabs(dphi2) <= gmax) || !(S.f2 <= top);
+                            const bool use0 = A0 || B0, use1 = (A1 && !A0) || (B1 && !B0);
+                            dead = (!use0 || never0) && (!use1 || never1);
+                        }
+                    }
+#endif
+                    if (dead || !isfinite(stp) || S.w1_it >= 100) start_w2 = 1;  // WARN / maxiter -> stp None
                     else alpha = stp;
                 }
             } else if (ls == LS_W2) {
