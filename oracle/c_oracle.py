@@ -37,8 +37,18 @@ def lib():
         L.stm_oracle_bfgs.argtypes = [C.c_int, C.c_int, dp, dp, dp, dp, dp, dp,
                                       C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]
         L.stm_oracle_bfgs.restype = C.c_int
+        L.stm_oracle_tail_check.argtypes = [C.c_int, C.POINTER(C.c_longlong)]
+        L.stm_oracle_tail_check.restype = None
         _lib = L
     return _lib
+
+
+def tail_check(enable):
+    """Switch the oracle's self-check of the kernel's DCSRCH tail shortcut on / off; returns the counters gathered
+    since the last call: dict(fired, accept_after, third_vector, skipped_trials)."""
+    out = (C.c_longlong * 4)()
+    lib().stm_oracle_tail_check(int(bool(enable)), out)
+    return dict(fired=out[0], accept_after=out[1], third_vector=out[2], skipped_trials=out[3])
 
 
 def _p(a, t):

@@ -142,6 +142,20 @@ static void precompute_a(doc_t *p) {
     }
 }
 
+/* Optional self-check of a shortcut the CUDA kernel takes (estep_kernel.cuh, STM_W1_TAIL_SKIP): a DCSRCH search is
+ * abandoned for Wolfe-2 as soon as the trial vectors at the two ends of its bracket differ in at most one component and
+ * neither of them can pass the convergence test for any step of the bracket.  With the check enabled the oracle
+ * evaluates that rule at every iteration (on fresh evaluations of the two vectors, outside the memo: nfev / njev are not
+ * touched), keeps replaying the search as SciPy does, and counts the searches in which the rule fired and those of them
+ * that went on to ACCEPT a step or to evaluate a third vector: both must stay 0 for the shortcut to be exact. */
+static int tail_check_on = 0;
+static long long tail_fired = 0, tail_accept_after = 0, tail_third_vector = 0, tail_skipped_trials = 0;
+void stm_oracle_tail_check(int enable, long long *out4) {
+    if (out4) { out4[0] = tail_fired; out4[1] = tail_accept_after; out4[2] = tail_third_vector; out4[3] = tail_skipped_trials; }
+    tail_check_on = enable;
+    tail_fired = tail_accept_after = tail_third_vector = tail_skipped_trials = 0;
+}
+
 static int vec_equal(const double *a, const double *b, int n) {
     for (int i = 0; i < n; ++i) if (!(a[i] == b[i])) return 0;
     return 1;
@@ -289,6 +303,8 @@ static int search_wolfe1(line_t *L, double phi0, double old_phi0, double derphi0
     double width = stpmax - stpmin, width1 = width / 0.5;
     double stx = 0.0, fx = finit, gx = ginit, sty = 0.0, fy = finit, gy = ginit;
     double stmin = 0, stmax = stp + 4.0 * stp;
+    int fired = 0;
+    double *ends = NULL; /* tail check: the two end vectors of the bracket when the rule fired */
 
     /* DCSRCH.__call__: for i in range(maxiter=100); i = 0 was START */
     for (int it = 0; it < 100; ++it) {
@@ -302,8 +318,12 @@ static int search_wolfe1(line_t *L, double phi0, double old_phi0, double derphi0
             if (stp == stpmax && f <= ftest && g <= gtest) warn = 1;
             if (stp == stpmin && (f > ftest || g >= gtest)) warn = 1;
             if (f <= ftest && fabs(g) <= gtol * -ginit) conv = 1;
-            if (conv) { *alpha = stp; *phi1_out = f; return isfinite(stp) ? 1 : 0; }
-            if (warn) return 0;
+            if (conv) {
+                if (fired) __sync_fetch_and_add(&tail_accept_after, 1);
+                free(ends);
+                *alpha = stp; *phi1_out = f; return isfinite(stp) ? 1 : 0;
+            }
+            if (warn) { free(ends); return 0; }
 
             if (stage == 1 && f <= fx && f > ftest) {
                 double fm = f - stp * gtest, fxm = fx - stx * gtest, fym = fy - sty * gtest;
@@ -330,12 +350,43 @@ static int search_wolfe1(line_t *L, double phi0, double old_phi0, double derphi0
             if ((brackt && (stp <= stmin || stp >= stmax)) ||
                 (brackt && stmax - stmin <= xtol * stmax))
                 stp = stx;
+            if (tail_check_on && brackt && !fired) {
+                const int n = L->p->K1;
+                double *e2 = (double *)malloc(sizeof(double) * 3 * (size_t)n), *gg = e2 + 2 * n;
+                int nd = 0;
+                for (int i = 0; i < n; ++i) {
+                    e2[i] = L->xk[i] + stmin * L->pk[i];
+                    e2[n + i] = L->xk[i] + stmax * L->pk[i];
+                    nd += !(e2[i] == e2[n + i]);
+                }
+                int never = nd <= 1;
+                for (int e = 0; never && e < (nd ? 2 : 1); ++e) {
+                    const double fp = obj_f(L->p, e2 + e * n);
+                    obj_df(L->p, e2 + e * n, gg);
+                    double gd = 0.0;
+                    for (int i = 0; i < n; ++i) gd += gg[i] * L->pk[i];
+                    never = !(fabs(gd) <= gtol * -ginit) || !(fp <= finit + stmin * gtest);
+                }
+                if (never) { fired = 1; ends = e2; __sync_fetch_and_add(&tail_fired, 1); }
+                else free(e2);
+            }
         }
-        if (!isfinite(stp)) return 0;
+        if (!isfinite(stp)) { free(ends); return 0; }
+        if (fired) {
+            const int n = L->p->K1;
+            int third = 0;
+            for (int i = 0; i < n && !third; ++i) {
+                const double xi = L->xk[i] + stp * L->pk[i];
+                third = !(xi == ends[i]) && !(xi == ends[n + i]);
+            }
+            if (third) __sync_fetch_and_add(&tail_third_vector, 1);
+            __sync_fetch_and_add(&tail_skipped_trials, 1);
+        }
         /* task == FG */
         f = ls_phi(L, stp);
         g = ls_derphi(L, stp);
     }
+    free(ends);
     return 0; /* maxiter reached */
 }
 

@@ -816,6 +816,9 @@ __global__ void __launch_bounds__(STM_BFGS_MAX_THREADS, 1) bfgs_kernel(const Est
                 const bool hit0 = __all_sync(STM_FULL, same0);
                 const bool hit1 = !hit0 && __all_sync(STM_FULL, same1);
                 memo_hit = hit0 || hit1;
+#if STM_DBG_TIMING
+                dbg_t[14] += 1; dbg_t[15] += memo_hit ? 1 : 0;   // slots 14 / 15: steps, memo hits
+#endif
                 if (hit1) {
 #pragma unroll
                     for (int i = 0; i < KPL; ++i) {

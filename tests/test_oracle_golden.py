@@ -193,6 +193,36 @@ def test_pd_test_by_pivots_equals_true_eigenvalues():
         assert np.abs(c["eta"][sel] - o["eta"][sel]).max() < 1e-8
 
 
+def test_dcsrch_tail_shortcut_rule_is_exact_on_the_oracle():
+    """The CUDA kernel abandons a DCSRCH search for Wolfe-2 once the bracket has collapsed onto at most two neighbouring
+    trial vectors that can never pass the convergence test (estep_kernel.cuh, STM_W1_TAIL_SKIP).  The oracle replays
+    every search as SciPy does and checks the rule on the way (oracle/stm_oracle.c, stm_oracle_tail_check): on K=50 and
+    K=20 states where every document ends in a failing search, the rule fires in (nearly) every document, and never
+    before an acceptance or a third trial vector; enabling the check changes no result."""
+    from conftest import unpack_corpus
+    for name, key, D, n_iter in (("em_k50.npz", "beta0", 1500, 2), ("em_c2.npz", "cut_beta0", None, 3)):
+        g = load_golden(name)
+        D = D or int(g["cut"])
+        ptr, ids, cnt = unpack_corpus(g, D)
+        X = g["X"][:D]
+        run = lambda *a, **k: c_oracle.estep(*a, nthreads=4, **k)
+        ref = stm_numpy.em(ptr, ids, cnt, g[key].astype(np.float64), X, n_iter=n_iter, estep_fn=run,
+                           round_beta32=True, keep_states=True)
+        st = ref["states"][-1]
+        siginv, ent = stm_numpy.prologue(st["sigma"])
+        plain = c_oracle.estep(ptr, ids, cnt, st["beta"], st["mu"], siginv, ent, st["eta"], nthreads=4)
+        c_oracle.tail_check(True)
+        try:
+            checked = c_oracle.estep(ptr, ids, cnt, st["beta"], st["mu"], siginv, ent, st["eta"], nthreads=4)
+        finally:
+            cnts = c_oracle.tail_check(False)
+        assert cnts["fired"] > 0.5 * D, (name, cnts)
+        assert cnts["skipped_trials"] > 5 * cnts["fired"], (name, cnts)
+        assert cnts["accept_after"] == 0 and cnts["third_vector"] == 0, (name, cnts)
+        for k in ("eta", "doc_bound", "status", "nit", "nfev", "njev"):
+            np.testing.assert_array_equal(plain[k], checked[k])
+
+
 def test_em_toy_ctm_trace_c_oracle():
     g = load_golden("em_toy_ctm.npz")
     run = lambda *a, **k: c_oracle.estep(*a, **k)

@@ -75,7 +75,7 @@ def main():
             else:
                 tot = sum(arr[:8]) or 1
                 names = ["gather+a_k", "eval", "linesearch", "accept/Hupd", "theta", "colsum+hess", "chol", "bound+inv+nu",
-                         "e:memo+max", "e:exp", "e:contract+lp", "e:log(prod)", "e:reduce", "e:lse+grad", "-", "-"]
+                         "e:memo+max", "e:exp", "e:contract+lp", "e:log(prod)", "e:reduce", "e:lse+grad", "#steps", "#memo"]
                 out.append("      cycles/doc/warp: " + "  ".join(f"{nm} {c/len(d['nfev']):.0f} ({c/tot*100:.0f}%)" for nm, c in zip(names, arr)))
         except AttributeError:
             pass
