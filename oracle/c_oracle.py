@@ -44,11 +44,14 @@ def lib():
 
 
 def tail_check(enable):
-    """Switch the oracle's self-check of the kernel's DCSRCH tail shortcut on / off; returns the counters gathered
-    since the last call: dict(fired, accept_after, third_vector, skipped_trials)."""
-    out = (C.c_longlong * 4)()
+    """Switch the oracle's self-check of the kernel's line-search shortcuts on / off; returns the counters gathered
+    since the last call (DCSRCH tail rule: fired, accept_after, third_vector, skipped_trials; curvature certificate:
+    cert_w1_fired, cert_w1_accept_after, cert_zoom_fired, cert_zoom_accept_after, cert_trials_skipped)."""
+    out = (C.c_longlong * 9)()
     lib().stm_oracle_tail_check(int(bool(enable)), out)
-    return dict(fired=out[0], accept_after=out[1], third_vector=out[2], skipped_trials=out[3])
+    keys = ("fired", "accept_after", "third_vector", "skipped_trials", "cert_w1_fired", "cert_w1_accept_after",
+            "cert_zoom_fired", "cert_zoom_accept_after", "cert_trials_skipped")
+    return dict(zip(keys, out))
 
 
 def _p(a, t):

@@ -150,10 +150,23 @@ static void precompute_a(doc_t *p) {
  * that went on to ACCEPT a step or to evaluate a third vector: both must stay 0 for the shortcut to be exact. */
 static int tail_check_on = 0;
 static long long tail_fired = 0, tail_accept_after = 0, tail_third_vector = 0, tail_skipped_trials = 0;
-void stm_oracle_tail_check(int enable, long long *out4) {
-    if (out4) { out4[0] = tail_fired; out4[1] = tail_accept_after; out4[2] = tail_third_vector; out4[3] = tail_skipped_trials; }
+/* Second shortcut of the kernel (STM_CURV_CERT): the reference's gradient is the gradient of a CONVEX function h (the
+ * data term of df is not weighted by exp(eta), stm.py:954), so phi'(alpha) = g(x + alpha p).p cannot rise by more than
+ * alpha*C, C = p'Sp + N min(max p_k^2, |p|^2/2), and for alpha <= a_safe = 0.05|phi'(0)|/C the strong-Wolfe curvature
+ * test |phi'(alpha)| <= 0.9|phi'(0)| - part of every acceptance test - cannot pass.  The kernel ends DCSRCH (bracket
+ * set) and _zoom as soon as their bracket lies inside [0, a_safe].  Checked here the same way: replay in full, count
+ * the searches in which the certificate held and those of them that accepted a step afterwards (must be 0). */
+static long long cert_w1_fired = 0, cert_w1_accept_after = 0, cert_zoom_fired = 0, cert_zoom_accept_after = 0;
+static long long cert_trials_skipped = 0;
+void stm_oracle_tail_check(int enable, long long *out9) {
+    if (out9) {
+        out9[0] = tail_fired; out9[1] = tail_accept_after; out9[2] = tail_third_vector; out9[3] = tail_skipped_trials;
+        out9[4] = cert_w1_fired; out9[5] = cert_w1_accept_after; out9[6] = cert_zoom_fired;
+        out9[7] = cert_zoom_accept_after; out9[8] = cert_trials_skipped;
+    }
     tail_check_on = enable;
     tail_fired = tail_accept_after = tail_third_vector = tail_skipped_trials = 0;
+    cert_w1_fired = cert_w1_accept_after = cert_zoom_fired = cert_zoom_accept_after = cert_trials_skipped = 0;
 }
 
 static int vec_equal(const double *a, const double *b, int n) {
@@ -188,6 +201,7 @@ typedef struct {
     double *xt;   /* K1 trial point                    */
     double *gval; /* K1 gradient at last derphi() call */
     int have_gval;
+    double a_safe; /* curvature certificate of the current direction (0 = none); only used by the self-check */
 } line_t;
 
 static double ls_phi(line_t *L, double s) {
@@ -303,7 +317,7 @@ static int search_wolfe1(line_t *L, double phi0, double old_phi0, double derphi0
     double width = stpmax - stpmin, width1 = width / 0.5;
     double stx = 0.0, fx = finit, gx = ginit, sty = 0.0, fy = finit, gy = ginit;
     double stmin = 0, stmax = stp + 4.0 * stp;
-    int fired = 0;
+    int fired = 0, certw = 0;
     double *ends = NULL; /* tail check: the two end vectors of the bracket when the rule fired */
 
     /* DCSRCH.__call__: for i in range(maxiter=100); i = 0 was START */
@@ -319,6 +333,7 @@ static int search_wolfe1(line_t *L, double phi0, double old_phi0, double derphi0
             if (stp == stpmin && (f > ftest || g >= gtest)) warn = 1;
             if (f <= ftest && fabs(g) <= gtol * -ginit) conv = 1;
             if (conv) {
+                if (certw) __sync_fetch_and_add(&cert_w1_accept_after, 1);
                 if (fired) __sync_fetch_and_add(&tail_accept_after, 1);
                 free(ends);
                 *alpha = stp; *phi1_out = f; return isfinite(stp) ? 1 : 0;
@@ -350,6 +365,10 @@ static int search_wolfe1(line_t *L, double phi0, double old_phi0, double derphi0
             if ((brackt && (stp <= stmin || stp >= stmax)) ||
                 (brackt && stmax - stmin <= xtol * stmax))
                 stp = stx;
+            if (tail_check_on && brackt && !certw && L->a_safe > 0.0 && stmax <= L->a_safe) {
+                certw = 1;
+                __sync_fetch_and_add(&cert_w1_fired, 1);
+            }
             if (tail_check_on && brackt && !fired) {
                 const int n = L->p->K1;
                 double *e2 = (double *)malloc(sizeof(double) * 3 * (size_t)n), *gg = e2 + 2 * n;
@@ -382,6 +401,7 @@ static int search_wolfe1(line_t *L, double phi0, double old_phi0, double derphi0
             if (third) __sync_fetch_and_add(&tail_third_vector, 1);
             __sync_fetch_and_add(&tail_skipped_trials, 1);
         }
+        if (certw) __sync_fetch_and_add(&cert_trials_skipped, 1);
         /* task == FG */
         f = ls_phi(L, stp);
         g = ls_derphi(L, stp);
@@ -427,7 +447,14 @@ static int zoom(line_t *L, double a_lo, double a_hi, double phi_lo, double phi_h
     const double delta1 = 0.2, delta2 = 0.1;
     double phi_rec = phi0, a_rec = 0;
     double a_j = NAN;
+    int certz = 0;
     for (;;) {
+        if (tail_check_on && !certz && L->a_safe > 0.0 && a_lo <= L->a_safe && a_hi <= L->a_safe &&
+            a_lo >= 0.0 && a_hi >= 0.0) {
+            certz = 1;
+            __sync_fetch_and_add(&cert_zoom_fired, 1);
+        }
+        if (certz) __sync_fetch_and_add(&cert_trials_skipped, 1);
         double dalpha = a_hi - a_lo, a, b, cchk = 0.0;
         if (dalpha < 0) { a = a_hi; b = a_lo; } else { a = a_lo; b = a_hi; }
         if (i > 0) {
@@ -444,7 +471,10 @@ static int zoom(line_t *L, double a_lo, double a_hi, double phi_lo, double phi_h
             phi_rec = phi_hi; a_rec = a_hi; a_hi = a_j; phi_hi = phi_aj;
         } else {
             double derphi_aj = ls_derphi(L, a_j);
-            if (fabs(derphi_aj) <= -c2 * derphi0) { *a_star = a_j; *val_star = phi_aj; return 1; }
+            if (fabs(derphi_aj) <= -c2 * derphi0) {
+                if (certz) __sync_fetch_and_add(&cert_zoom_accept_after, 1);
+                *a_star = a_j; *val_star = phi_aj; return 1;
+            }
             if (derphi_aj * (a_hi - a_lo) >= 0) {
                 phi_rec = phi_hi; a_rec = a_hi; a_hi = a_lo; phi_hi = phi_lo;
             } else {
@@ -527,6 +557,24 @@ static int bfgs(doc_t *p, double *x, double *work /* 6*n + 3*n*n */, double *fun
         double derphi0 = 0.0;
         for (int i = 0; i < n; ++i) derphi0 += gfk[i] * pk[i];
 
+        L.a_safe = 0.0;
+        if (tail_check_on) {
+            /* the kernel's formula and guard (estep_kernel.cuh, "curvature certificate") */
+            double pSp = 0.0, mx = 0.0, sm = 0.0, noise = 0.0;
+            for (int i = 0; i < n; ++i) {
+                double t = 0.0, sx = 0.0;
+                for (int j = 0; j < n; ++j) { t += p->S[(size_t)i * n + j] * pk[j]; sx += p->S[(size_t)i * n + j] * (x[j] - p->mu[j]); }
+                pSp += pk[i] * t;
+                if (pk[i] * pk[i] > mx) mx = pk[i] * pk[i];
+                sm += pk[i] * pk[i];
+                noise += fabs(pk[i]) * (fabs(sx) + fabs(p->a[i]) + p->Nsum);
+            }
+            const double Cc = pSp + p->Nsum * fmin(mx, 0.5 * sm);
+            if (derphi0 < 0.0 && Cc > 0.0 && Cc < 1e300 && 1e-12 * noise <= 0.01 * -derphi0) {
+                const double as = 0.05 * -derphi0 / Cc;
+                if (isfinite(as)) L.a_safe = as;
+            }
+        }
         double alpha_k = 0.0, new_fval = 0.0;
         int have_g = 0;
         int ok = search_wolfe1(&L, old_fval, old_old_fval, derphi0, &alpha_k, &new_fval);

@@ -65,6 +65,9 @@
 #define STM_DBG_SKIP_DENSE 0
 #endif
 #ifndef STM_BFGS_MAX_THREADS
+#ifndef STM_CURV_CERT
+#define STM_CURV_CERT 1       // 1: end a line search whose bracket lies where the curvature condition provably cannot hold (see
+#endif                        //    the comment at "curvature certificate" in kernel A)
 #ifndef STM_W1_TAIL_SKIP
 #define STM_W1_TAIL_SKIP 1    // 1: leave a DCSRCH search whose bracket has collapsed onto memoised points that can never be accepted
 #endif                        //    (exact: see the comment at the use; r02: kernel A 28.4 -> ... ms)
@@ -555,6 +558,7 @@ struct LsState {
     double finit, ginit, gtest, width, width1, stx, fx, gx, sty, fy, gy, stmin, stmax;
     // scalar_search_wolfe2 / _zoom (scipy/optimize/_linesearch.py)
     double alpha0, phi_a0, derphi_a0, a_lo, a_hi, phi_lo, phi_hi, derphi_lo, phi_rec, a_rec;
+    double a_safe;   // curvature certificate of the current direction (STM_CURV_CERT), 0 = none
     int brackt, stage, w1_it, w2_i, z_i, pad_;
 };
 
@@ -789,7 +793,7 @@ __global__ void __launch_bounds__(STM_BFGS_MAX_THREADS, 1) bfgs_kernel(const Est
         int dphi_ok = 0, dphi2_ok = 0;
         if (STM_LS_REGS || lane == 0) {
             S.old_fval = 0.0; S.old_old_fval = 0.0; S.gnorm = 0.0; S.derphi0 = 0.0; S.f2 = 0.0;
-            S.brackt = 0; S.stage = 1; S.w1_it = 0; S.w2_i = 0; S.z_i = 0;
+            S.brackt = 0; S.stage = 1; S.w1_it = 0; S.w2_i = 0; S.z_i = 0; S.a_safe = 0.0;
         }
         __syncwarp();
 
@@ -1128,6 +1132,9 @@ __global__ void __launch_bounds__(STM_BFGS_MAX_THREADS, 1) bfgs_kernel(const Est
                         }
                     }
 #endif
+#if STM_CURV_CERT
+                    if (S.brackt && S.a_safe > 0.0 && S.stmax <= S.a_safe) dead = true;   // curvature certificate: cannot converge any more
+#endif
                     if (dead || !isfinite(stp) || S.w1_it >= 100) start_w2 = 1;  // WARN / maxiter -> stp None
                     else alpha = stp;
                 }
@@ -1188,6 +1195,14 @@ __global__ void __launch_bounds__(STM_BFGS_MAX_THREADS, 1) bfgs_kernel(const Est
                 S.phi_rec = S.old_fval; S.a_rec = 0.0; S.z_i = 0;
                 ls = LS_ZOOM;
             }
+#if STM_CURV_CERT
+            // curvature certificate: _zoom's trials stay inside [a_lo, a_hi] (cubic / quadratic steps are range-checked,
+            // else bisection), the interval only shrinks, and no step in it can be accepted: _zoom will run out of
+            // iterations and return None
+            if (ls == LS_ZOOM && !accept && !fail && S.a_safe > 0.0 && S.a_lo <= S.a_safe && S.a_hi <= S.a_safe &&
+                S.a_lo >= 0.0 && S.a_hi >= 0.0)
+                fail = 1;
+#endif
             if (ls == LS_ZOOM && !accept && !fail) {
                 // next trial step of _zoom
                 const double dalpha = S.a_hi - S.a_lo;
@@ -1307,6 +1322,42 @@ __global__ void __launch_bounds__(STM_BFGS_MAX_THREADS, 1) bfgs_kernel(const Est
 #pragma unroll
                     for (int i = 0; i < KPL; ++i) d_l += g[i] * p[i];
                     S.derphi0 = warp_sum(d_l);
+#if STM_CURV_CERT
+                    // ---- curvature certificate -----------------------------------------------------------------
+                    // The reference's gradient (stm.py:946-958) is NOT the gradient of its objective but of the convex
+                    //   h(eta) = 1/2 (eta-mu)' S (eta-mu) - a' eta + N logsumexp([eta, 0])
+                    // (SURVEY 8a, a6), so phi'(alpha) = g(x + alpha p) . p is non-decreasing in alpha and
+                    //   phi'(alpha) - phi'(0) = int_0^alpha p' grad^2 h p dt <= alpha C,
+                    //   C = p' S p + N min(max_k p_k^2, 1/2 |p|^2)        (diag(theta) - theta theta' <= diag(theta), sum theta <= 1).
+                    // Every acceptance test of the three searches contains the strong-Wolfe curvature condition
+                    // |phi'(alpha)| <= 0.9 |phi'(0)| (_dcsrch.py:373, _linesearch.py:433, :606).  For
+                    // alpha <= a_safe = 0.05 |phi'(0)| / C the exact phi'(alpha) lies in [phi'(0), 0.95 phi'(0)], so the
+                    // test fails with a margin of 0.05 |phi'(0)| — more than 1e4 times any rounding error of an fp64
+                    // evaluation of g . p, which the guard below bounds by 1e-12 sum_i |p_i| (|S (x-mu)|_i + |a_i| + N)
+                    // and requires to be below 0.01 |phi'(0)| (otherwise no certificate: a_safe = 0).
+                    // Consequence: once a search's bracket lies inside [0, a_safe] and can only shrink (DCSRCH with
+                    // brackt set; _zoom always), no later trial can be accepted and the search is known to fail —
+                    // which is all that is left of it: a failed DCSRCH hands nothing to Wolfe-2, a failed _zoom raises
+                    // _LineSearchError and BFGS returns the current x (_optimize.py:1446-1449).  The C oracle replays
+                    // every search in full and checks this rule on the way (stm_oracle_tail_check): 0 acceptances
+                    // after the certificate in every state of tests/ and tools/.
+                    {
+                        double c_l = 0.0, s_l = 0.0, m_l = 0.0, n_l = 0.0;
+#pragma unroll
+                        for (int i = 0; i < KPL; ++i) {
+                            const double pp = p[i] * p[i];
+                            c_l += Sd[i] * pp; s_l += pp; m_l = fmax(m_l, pp);
+                            n_l += fabs(p[i]) * (fabs(Sd[i] * (x[i] - mu[i])) + fabs(a[i]) + Nsum);
+                        }
+                        const double pSp = warp_sum(c_l), pp2 = warp_sum(s_l), noise = 1e-12 * warp_sum(n_l);
+                        const double pmax2 = warp_max(m_l);
+                        const double Cc = pSp + Nsum * fmin(pmax2, 0.5 * pp2);
+                        double as = 0.0;
+                        if (S.derphi0 < 0.0 && Cc > 0.0 && Cc < 1e300 && noise <= 0.01 * -S.derphi0)
+                            as = ddiv(0.05 * -S.derphi0, Cc);
+                        S.a_safe = isfinite(as) ? as : 0.0;
+                    }
+#endif
                     // scalar_search_wolfe1 prologue + DCSRCH START
                     double alpha1;
                     if (S.derphi0 != 0.0) {

@@ -193,12 +193,17 @@ def test_pd_test_by_pivots_equals_true_eigenvalues():
         assert np.abs(c["eta"][sel] - o["eta"][sel]).max() < 1e-8
 
 
-def test_dcsrch_tail_shortcut_rule_is_exact_on_the_oracle():
-    """The CUDA kernel abandons a DCSRCH search for Wolfe-2 once the bracket has collapsed onto at most two neighbouring
-    trial vectors that can never pass the convergence test (estep_kernel.cuh, STM_W1_TAIL_SKIP).  The oracle replays
-    every search as SciPy does and checks the rule on the way (oracle/stm_oracle.c, stm_oracle_tail_check): on K=50 and
-    K=20 states where every document ends in a failing search, the rule fires in (nearly) every document, and never
-    before an acceptance or a third trial vector; enabling the check changes no result."""
+def test_line_search_shortcuts_are_exact_on_the_oracle():
+    """The CUDA kernel does not replay the part of a failing line search whose outcome is already decided:
+    (a) curvature certificate (estep_kernel.cuh, STM_CURV_CERT): the reference's gradient is the gradient of a convex
+        function, so for steps below a_safe = 0.05 |phi'(0)| / (p'Sp + N min(max p_k^2, |p|^2/2)) the strong-Wolfe
+        curvature condition cannot hold; DCSRCH (bracket set) and _zoom are ended once their bracket lies in [0, a_safe];
+    (b) tail rule (STM_W1_TAIL_SKIP): DCSRCH is ended once its bracket has collapsed onto at most two neighbouring
+        trial vectors that can never pass the convergence test.
+    The oracle replays every search as SciPy does and checks both rules on the way (oracle/stm_oracle.c,
+    stm_oracle_tail_check): on K=50 and K=20 states where every document ends in a failing search the rules hold in
+    (nearly) every document and are never followed by an acceptance (or, for (b), a third trial vector); enabling the
+    check changes no result."""
     from conftest import unpack_corpus
     for name, key, D, n_iter in (("em_k50.npz", "beta0", 1500, 2), ("em_c2.npz", "cut_beta0", None, 3)):
         g = load_golden(name)
@@ -219,6 +224,9 @@ def test_dcsrch_tail_shortcut_rule_is_exact_on_the_oracle():
         assert cnts["fired"] > 0.5 * D, (name, cnts)
         assert cnts["skipped_trials"] > 5 * cnts["fired"], (name, cnts)
         assert cnts["accept_after"] == 0 and cnts["third_vector"] == 0, (name, cnts)
+        assert cnts["cert_w1_fired"] > 0.8 * D and cnts["cert_zoom_fired"] > 0.8 * D, (name, cnts)
+        assert cnts["cert_trials_skipped"] > 30 * D, (name, cnts)
+        assert cnts["cert_w1_accept_after"] == 0 and cnts["cert_zoom_accept_after"] == 0, (name, cnts)
         for k in ("eta", "doc_bound", "status", "nit", "nfev", "njev"):
             np.testing.assert_array_equal(plain[k], checked[k])
 
