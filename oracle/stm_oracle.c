@@ -152,7 +152,8 @@ static int tail_check_on = 0;
 static long long tail_fired = 0, tail_accept_after = 0, tail_third_vector = 0, tail_skipped_trials = 0;
 /* Second shortcut of the kernel (STM_CURV_CERT): the reference's gradient is the gradient of a CONVEX function h (the
  * data term of df is not weighted by exp(eta), stm.py:954), so phi'(alpha) = g(x + alpha p).p cannot rise by more than
- * alpha*C, C = p'Sp + N min(max p_k^2, |p|^2/2), and for alpha <= a_safe = 0.05|phi'(0)|/C the strong-Wolfe curvature
+ * alpha*C, C = p'Sp + N min(max p_k^2, |p|^2/2) (or p'Sp + 1.11 N Var_theta(x)([p,0]) while alpha (max pt - min pt) <= 0.1),
+ * and for alpha <= a_safe = 0.09|phi'(0)|/C the strong-Wolfe curvature
  * test |phi'(alpha)| <= 0.9|phi'(0)| - part of every acceptance test - cannot pass.  The kernel ends DCSRCH (bracket
  * set) and _zoom as soon as their bracket lies inside [0, a_safe].  Checked here the same way: replay in full, count
  * the searches in which the certificate held and those of them that accepted a step afterwards (must be 0). */
@@ -559,19 +560,34 @@ static int bfgs(doc_t *p, double *x, double *work /* 6*n + 3*n*n */, double *fun
 
         L.a_safe = 0.0;
         if (tail_check_on) {
-            /* the kernel's formula and guard (estep_kernel.cuh, "curvature certificate") */
-            double pSp = 0.0, mx = 0.0, sm = 0.0, noise = 0.0;
+            /* the kernel's formula and guard (estep_kernel.cuh, "curvature certificate"): bound (i) on the variance
+             * term, and bound (ii) from theta at x */
+            double pSp = 0.0, mx = 0.0, sm = 0.0, noise = 0.0, hi = 0.0, lo = 0.0, xm = 0.0;
             for (int i = 0; i < n; ++i) {
                 double t = 0.0, sx = 0.0;
                 for (int j = 0; j < n; ++j) { t += p->S[(size_t)i * n + j] * pk[j]; sx += p->S[(size_t)i * n + j] * (x[j] - p->mu[j]); }
                 pSp += pk[i] * t;
                 if (pk[i] * pk[i] > mx) mx = pk[i] * pk[i];
+                if (pk[i] > hi) hi = pk[i];
+                if (-pk[i] > lo) lo = -pk[i];
+                if (x[i] > xm) xm = x[i];
                 sm += pk[i] * pk[i];
                 noise += fabs(pk[i]) * (fabs(sx) + fabs(p->a[i]) + p->Nsum);
             }
-            const double Cc = pSp + p->Nsum * fmin(mx, 0.5 * sm);
-            if (derphi0 < 0.0 && Cc > 0.0 && Cc < 1e300 && 1e-12 * noise <= 0.01 * -derphi0) {
-                const double as = 0.05 * -derphi0 / Cc;
+            const double C1 = pSp + p->Nsum * fmin(mx, 0.5 * sm);
+            if (derphi0 < 0.0 && C1 > 0.0 && C1 < 1e300 && 1e-12 * noise <= 0.01 * -derphi0) {
+                const double num = 0.09 * -derphi0;
+                double as = num / C1;
+                double se = exp(0.0 - xm), m1 = 0.0, v0 = 0.0;
+                for (int i = 0; i < n; ++i) se += exp(x[i] - xm);
+                for (int i = 0; i < n; ++i) m1 += exp(x[i] - xm) / se * pk[i];
+                for (int i = 0; i < n; ++i) v0 += exp(x[i] - xm) / se * (pk[i] - m1) * (pk[i] - m1);
+                v0 += exp(0.0 - xm) / se * m1 * m1;
+                const double C2 = pSp + 1.1100001 * p->Nsum * v0, R = hi + lo;
+                if (C2 > 0.0 && v0 >= 0.0 && R > 0.0 && R < 1e300) {
+                    const double as2 = fmin(num / C2, 0.1 / R);
+                    if (as2 > as) as = as2;
+                }
                 if (isfinite(as)) L.a_safe = as;
             }
         }

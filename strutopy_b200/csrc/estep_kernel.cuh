@@ -786,6 +786,10 @@ __global__ void __launch_bounds__(STM_BFGS_MAX_THREADS, 1) bfgs_kernel(const Est
         const int maxiter = K1 * 200;
         double alpha = 0.0, f_eval = 0.0, dphi = 0.0;
         int have_cache = 0, have_cache2 = 0;
+        // ex[] / scale_e (= N / sum exp) belong to memo entry ex_owner (0: xt, 1: xt2, -1: neither): the curvature
+        // certificate wants theta at the base point of the new search, which is the accepted trial xt
+        int ex_owner = -1;
+        double scale_e = 0.0;
         // phi'(alpha) = g . p of the two memoised points: what SciPy's memoised gradient gives back for a repeated
         // trial point is the SAME value as the first time, so the value of the fresh evaluation is kept (and the
         // memo-hit path no longer runs a reduction); invalid after the direction p has changed
@@ -833,6 +837,7 @@ __global__ void __launch_bounds__(STM_BFGS_MAX_THREADS, 1) bfgs_kernel(const Est
                     const double td = dphi; dphi = dphi2; dphi2 = td;
                     const int tk = dphi_ok; dphi_ok = dphi2_ok; dphi2_ok = tk;
                     have_cache2 = have_cache;  // both valid after a swap
+                    ex_owner = (ex_owner >= 0) ? 1 - ex_owner : -1;
                 }
                 if (!hit0 && !hit1) {
 #pragma unroll
@@ -842,6 +847,7 @@ __global__ void __launch_bounds__(STM_BFGS_MAX_THREADS, 1) bfgs_kernel(const Est
                     have_cache2 = have_cache;
                     nfev++;
                     have_cache = 1;
+                    ex_owner = 0;
                     double et[KPL];
                     double m = -INFINITY;
 #pragma unroll
@@ -985,6 +991,7 @@ __global__ void __launch_bounds__(STM_BFGS_MAX_THREADS, 1) bfgs_kernel(const Est
 
                     // gradient stm.py:946-958 (beta NOT weighted by exp(eta): reference quirk)
                     const double scale = ddiv(Nsum, se_all);
+                    scale_e = scale;
 #pragma unroll
                     for (int i = 0; i < KPL; ++i) {
                         const int k = lane + 32 * i;
@@ -1327,14 +1334,17 @@ __global__ void __launch_bounds__(STM_BFGS_MAX_THREADS, 1) bfgs_kernel(const Est
                     // The reference's gradient (stm.py:946-958) is NOT the gradient of its objective but of the convex
                     //   h(eta) = 1/2 (eta-mu)' S (eta-mu) - a' eta + N logsumexp([eta, 0])
                     // (SURVEY 8a, a6), so phi'(alpha) = g(x + alpha p) . p is non-decreasing in alpha and
-                    //   phi'(alpha) - phi'(0) = int_0^alpha p' grad^2 h p dt <= alpha C,
-                    //   C = p' S p + N min(max_k p_k^2, 1/2 |p|^2)        (diag(theta) - theta theta' <= diag(theta), sum theta <= 1).
+                    //   phi'(alpha) - phi'(0) = int_0^alpha [ p'Sp + N Var_theta(t)(pt) ] dt,   pt = [p, 0],
+                    // theta(t) = softmax([x + t p, 0]).  Two bounds on the variance term, valid for every t:
+                    //   (i)  Var <= min(max_k pt_k^2, 1/2 |p|^2)             (diag(theta) - theta theta' <= diag(theta), norm <= 1/2)
+                    //   (ii) Var_theta(t) <= e^{tR} Var_theta(0),  R = max pt - min pt   (theta_k(t) <= e^{tR} theta_k(0));
+                    //        e^{tR} <= 1.11 while t R <= 0.1.
                     // Every acceptance test of the three searches contains the strong-Wolfe curvature condition
-                    // |phi'(alpha)| <= 0.9 |phi'(0)| (_dcsrch.py:373, _linesearch.py:433, :606).  For
-                    // alpha <= a_safe = 0.05 |phi'(0)| / C the exact phi'(alpha) lies in [phi'(0), 0.95 phi'(0)], so the
-                    // test fails with a margin of 0.05 |phi'(0)| — more than 1e4 times any rounding error of an fp64
-                    // evaluation of g . p, which the guard below bounds by 1e-12 sum_i |p_i| (|S (x-mu)|_i + |a_i| + N)
-                    // and requires to be below 0.01 |phi'(0)| (otherwise no certificate: a_safe = 0).
+                    // |phi'(alpha)| <= 0.9 |phi'(0)| (_dcsrch.py:373, _linesearch.py:433, :606).  For alpha <= a_safe =
+                    // 0.09 |phi'(0)| / C (C from (i), or from (ii) with a_safe R <= 0.1) the exact phi'(alpha) lies in
+                    // [phi'(0), 0.91 phi'(0)], so the test fails by a margin of 0.01 |phi'(0)|.  The guard below bounds the
+                    // rounding error of ANY fp64 evaluation of g . p by 1e-12 sum_i |p_i| (|S (x-mu)|_i + |a_i| + N) — four
+                    // orders above the real thing — and gives no certificate (a_safe = 0) unless that is below the margin.
                     // Consequence: once a search's bracket lies inside [0, a_safe] and can only shrink (DCSRCH with
                     // brackt set; _zoom always), no later trial can be accepted and the search is known to fail —
                     // which is all that is left of it: a failed DCSRCH hands nothing to Wolfe-2, a failed _zoom raises
@@ -1342,19 +1352,40 @@ __global__ void __launch_bounds__(STM_BFGS_MAX_THREADS, 1) bfgs_kernel(const Est
                     // every search in full and checks this rule on the way (stm_oracle_tail_check): 0 acceptances
                     // after the certificate in every state of tests/ and tools/.
                     {
-                        double c_l = 0.0, s_l = 0.0, m_l = 0.0, n_l = 0.0;
+                        const bool th_ok = (ex_owner == 0);   // ex[], scale_e describe theta at x
+                        double c_l = 0.0, s_l = 0.0, n_l = 0.0, m_l = 0.0, hi_l = 0.0, lo_l = 0.0;
 #pragma unroll
                         for (int i = 0; i < KPL; ++i) {
+                            const int k = lane + 32 * i;
                             const double pp = p[i] * p[i];
-                            c_l += Sd[i] * pp; s_l += pp; m_l = fmax(m_l, pp);
+                            c_l += Sd[i] * pp; s_l += pp;
+                            hi_l = fmax(hi_l, p[i]); lo_l = fmax(lo_l, -p[i]);
                             n_l += fabs(p[i]) * (fabs(Sd[i] * (x[i] - mu[i])) + fabs(a[i]) + Nsum);
+                            if (k < K) m_l += scale_e * ex[i] * p[i];
                         }
                         const double pSp = warp_sum(c_l), pp2 = warp_sum(s_l), noise = 1e-12 * warp_sum(n_l);
-                        const double pmax2 = warp_max(m_l);
-                        const double Cc = pSp + Nsum * fmin(pmax2, 0.5 * pp2);
+                        const double m1 = ddiv(warp_sum(m_l), Nsum);          // mean of pt under theta(0)
+                        const double phi = warp_max(hi_l), plo = warp_max(lo_l);   // max(pt), -min(pt)  (pt contains 0)
+                        double v_l = 0.0;
+#pragma unroll
+                        for (int i = 0; i < KPL; ++i) {
+                            const int k = lane + 32 * i;
+                            const double dk = p[i] - m1;
+                            if (k < K) v_l += scale_e * ex[i] * dk * dk;
+                        }
+                        const double NV0 = warp_sum(v_l);                       // N Var_theta(0)(pt)
+                        const double pmax2 = fmax(phi * phi, plo * plo), R = phi + plo;
+                        const double C1 = pSp + Nsum * fmin(pmax2, 0.5 * pp2);
                         double as = 0.0;
-                        if (S.derphi0 < 0.0 && Cc > 0.0 && Cc < 1e300 && noise <= 0.01 * -S.derphi0)
-                            as = ddiv(0.05 * -S.derphi0, Cc);
+                        if (S.derphi0 < 0.0 && C1 > 0.0 && C1 < 1e300 && noise <= 0.01 * -S.derphi0) {
+                            const double num = 0.09 * -S.derphi0;
+                            as = ddiv(num, C1);
+                            const double C2 = pSp + 1.1100001 * NV0;
+                            if (th_ok && C2 > 0.0 && NV0 >= 0.0 && R > 0.0 && R < 1e300) {
+                                const double as2 = py_min2(ddiv(num, C2), ddiv(0.1, R));
+                                if (as2 > as) as = as2;
+                            }
+                        }
                         S.a_safe = isfinite(as) ? as : 0.0;
                     }
 #endif
