@@ -546,8 +546,9 @@ def ours(args):
             pk = fp64_peak_tflops(torch, dev)
             ach = fpd * D / (pair_ms * 1e-3) / 1e12
             fp64 = {"achieved": ach, "peak": pk, "unit": "TFLOP/s", "frac": ach / pk, "flops_per_doc": fpd,
-                    "source": "executed DFMA/DADD/DMUL/DMMA thread instructions of the kernel pair (ncu, profiles/"
-                              "estep_dram_traffic.json) / live kernel time; peak = cuBLAS DGEMM 4096^3 measured now"}
+                    "source": "executed DFMA/DADD/DMUL/DMMA thread instructions of the kernel pair (ncu at EM iteration 1 of "
+                              "this workload, profiles/estep_dram_traffic.json) / live kernel time; peak = cuBLAS DGEMM "
+                              "4096^3 measured now"}
         # ---- CPU baseline + parity on a bounded sample ---------------------------------------------------
         cpu = None
         parity = None
@@ -616,12 +617,13 @@ def ours(args):
                          "bytes_per_doc": b_doc, "estep_ms_per_launch": pair_ms,
                          "kernel_ms": {"stm::bfgs_kernel": bfgs_ms_mean, "stm::post_group_kernel": post_ms_mean,
                                        "estep_call_incl_memsets_epilogue": estep_ms_mean},
-                         "dominant_kernel": "stm::bfgs_kernel",
-                         "dominant_kernel_share_of_estep": bfgs_ms_mean / pair_ms,
+                         "dominant_kernel": "stm::bfgs_kernel" if bfgs_ms_mean >= post_ms_mean else "stm::post_group_kernel",
+                         "dominant_kernel_share_of_estep": max(bfgs_ms_mean, post_ms_mean) / pair_ms,
                          "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s",
                          "fp64": fp64,
-                         "limiter": "instruction fetch: gcc__cache_requests_type_instruction at 98 % of its peak rate "
-                                    "(profiles/r02_tuning_log.md)"},
+                         "limiter": "kernel A: instruction fetch (gcc__cache_requests_type_instruction at 97 % of its peak "
+                                    "rate, no_instruction the first stall reason); kernel B: fixed-latency dependencies and "
+                                    "named barriers at IPC 1.8 (profiles/r02d_estep_pair_ncu_summary.txt, r02_tuning_log.md)"},
             "cpu_baseline": cpu,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "api": "stm_estep_host (C ABI, fp64 host buffers in the reference's layouts; corpus resident; "
