@@ -98,7 +98,10 @@ int stm_prologue(stm_ctx* ctx, const double* sigma_dev, double* prior_dev, int* 
  *   theta_dev    double [D][K]      out (stm.py:547-549)
  *   stats_dev    packed buffer; segments 0-3 are (re)written
  *   doc_bound_dev double [D]; doc_info_dev int32 [D] (status | nit<<4 | repair<<24);
- *   doc_nfev_dev int32 [D]          per-document diagnostics (always written) */
+ *   doc_nfev_dev int32 [D]          per-document diagnostics (always written).  doc_nfev counts the objective
+ *                                   evaluations the device made: fewer than SciPy's nfev, because trial points are
+ *                                   memoised two deep and a line search whose failure is already decided is not
+ *                                   replayed — status, nit and eta are those of the full replay */
 int stm_estep(stm_ctx* ctx, const float* beta_t_dev, const double* mu_dev, const double* prior_dev,
               double* eta_dev, double* theta_dev, double* stats_dev, double* doc_bound_dev,
               int32_t* doc_info_dev, int32_t* doc_nfev_dev, void* stream);

@@ -513,6 +513,39 @@ def test_doc_bound_and_repair_vs_numpy_port_true_eigenvalues(lib):
     ctx.close()
 
 
+def test_line_search_shortcuts_keep_every_outcome():
+    """Kernel A does not replay line searches whose failure is already decided (curvature certificate + DCSRCH tail
+    rule).  Against the C oracle, which replays every search in full as SciPy does: status, iteration count,
+    repair stage EQUAL for every document, eta and the per-document bounds at the usual tolerances — while the device
+    makes a fraction of the oracle's objective evaluations (the shortcut is what runs, not a dormant branch).  K=50
+    spectral-init states of EM iterations 0-2 and config 2's K=20 random-init states."""
+    from strutopy_b200 import STM
+    nt = os.cpu_count() or 4
+    run = lambda *a, **k: c_oracle.estep(*a, nthreads=nt, **k)  # noqa: E731
+    for name, key, D, its in (("em_k50.npz", "beta0", 2000, (0, 1, 2)), ("em_c2.npz", "cut_beta0", None, (0, 2))):
+        g = load_golden(name)
+        K, V = int(g["K"]), int(g["V"])
+        D = D or int(g["cut"])
+        ptr, ids, cnt = unpack_corpus(g, D)
+        X = g["X"][:D]
+        ref = stm_numpy.em(ptr, ids, cnt, g[key].astype(np.float64), X, n_iter=max(its) + 1, estep_fn=run,
+                           round_beta32=True, keep_states=True)
+        m = STM((ptr, ids, cnt), range(V), False, K, X, False, 5, 0, 1e-5, init_type="random", model_type="STM")
+        for t in its:
+            st = ref["states"][t]
+            siginv, ent = stm_numpy.prologue(st["sigma"])
+            c = run(ptr, ids, cnt, st["beta"], st["mu"], siginv, ent, st["eta"])
+            m.beta, m.mu, m.sigma, m.eta = st["beta"], st["mu"], st["sigma"], st["eta"]
+            m.E_step()
+            d = m.doc_diagnostics()
+            for k in ("status", "nit", "repair"):
+                np.testing.assert_array_equal(d[k], c[k])
+            assert np.abs(m.eta - c["eta"]).max() < 1e-6
+            assert abs(m.bound - c["bound"]) <= 1e-11 * abs(c["bound"])
+            assert np.mean(c["status"] == 2) > 0.9                       # (nearly) every document ends in a failing search
+            assert d["nfev"].mean() < 0.45 * c["nfev"].mean(), (d["nfev"].mean(), c["nfev"].mean())
+
+
 def test_em_trace_toy_ctm_vs_live_reference():
     """the reference's own integration test pipeline (tests/test_integration.py): K=3, CTM, 2 iterations"""
     g = load_golden("em_toy_ctm.npz")
