@@ -37,20 +37,19 @@ def lib():
         L.stm_oracle_bfgs.argtypes = [C.c_int, C.c_int, dp, dp, dp, dp, dp, dp,
                                       C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]
         L.stm_oracle_bfgs.restype = C.c_int
-        L.stm_oracle_tail_check.argtypes = [C.c_int, C.POINTER(C.c_longlong)]
-        L.stm_oracle_tail_check.restype = None
+        L.stm_oracle_shortcut_check.argtypes = [C.c_int, C.POINTER(C.c_longlong)]
+        L.stm_oracle_shortcut_check.restype = None
         _lib = L
     return _lib
 
 
-def tail_check(enable):
-    """Switch the oracle's self-check of the kernel's line-search shortcuts on / off; returns the counters gathered
-    since the last call (DCSRCH tail rule: fired, accept_after, third_vector, skipped_trials; curvature certificate:
-    cert_w1_fired, cert_w1_accept_after, cert_zoom_fired, cert_zoom_accept_after, cert_trials_skipped)."""
-    out = (C.c_longlong * 9)()
-    lib().stm_oracle_tail_check(int(bool(enable)), out)
-    keys = ("fired", "accept_after", "third_vector", "skipped_trials", "cert_w1_fired", "cert_w1_accept_after",
-            "cert_zoom_fired", "cert_zoom_accept_after", "cert_trials_skipped")
+def shortcut_check(enable):
+    """Switch the oracle's self-check of the kernel's curvature certificate on / off; returns the counters gathered
+    since the last call: cert_w1_fired, cert_w1_accept_after, cert_zoom_fired, cert_zoom_accept_after,
+    cert_trials_skipped."""
+    out = (C.c_longlong * 5)()
+    lib().stm_oracle_shortcut_check(int(bool(enable)), out)
+    keys = ("cert_w1_fired", "cert_w1_accept_after", "cert_zoom_fired", "cert_zoom_accept_after", "cert_trials_skipped")
     return dict(zip(keys, out))
 
 

@@ -142,31 +142,24 @@ static void precompute_a(doc_t *p) {
     }
 }
 
-/* Optional self-check of a shortcut the CUDA kernel takes (estep_kernel.cuh, STM_W1_TAIL_SKIP): a DCSRCH search is
- * abandoned for Wolfe-2 as soon as the trial vectors at the two ends of its bracket differ in at most one component and
- * neither of them can pass the convergence test for any step of the bracket.  With the check enabled the oracle
- * evaluates that rule at every iteration (on fresh evaluations of the two vectors, outside the memo: nfev / njev are not
- * touched), keeps replaying the search as SciPy does, and counts the searches in which the rule fired and those of them
- * that went on to ACCEPT a step or to evaluate a third vector: both must stay 0 for the shortcut to be exact. */
-static int tail_check_on = 0;
-static long long tail_fired = 0, tail_accept_after = 0, tail_third_vector = 0, tail_skipped_trials = 0;
-/* Second shortcut of the kernel (STM_CURV_CERT): the reference's gradient is the gradient of a CONVEX function h (the
- * data term of df is not weighted by exp(eta), stm.py:954), so phi'(alpha) = g(x + alpha p).p cannot rise by more than
- * alpha*C, C = p'Sp + N min(max p_k^2, |p|^2/2) (or p'Sp + 1.11 N Var_theta(x)([p,0]) while alpha (max pt - min pt) <= 0.1),
- * and for alpha <= a_safe = 0.09|phi'(0)|/C the strong-Wolfe curvature
- * test |phi'(alpha)| <= 0.9|phi'(0)| - part of every acceptance test - cannot pass.  The kernel ends DCSRCH (bracket
- * set) and _zoom as soon as their bracket lies inside [0, a_safe].  Checked here the same way: replay in full, count
- * the searches in which the certificate held and those of them that accepted a step afterwards (must be 0). */
+/* Optional self-check of the shortcut the CUDA kernel takes (estep_kernel.cuh, STM_CURV_CERT).  The reference's
+ * gradient is the gradient of a CONVEX function h (the data term of df is not weighted by exp(eta), stm.py:954), so
+ * phi'(alpha) = g(x + alpha p).p cannot rise by more than alpha*C, C = p'Sp + N min(max p_k^2, |p|^2/2) (or
+ * p'Sp + 1.11 N Var_theta(x)([p,0]) while alpha (max pt - min pt) <= 0.1), and for alpha <= a_safe = 0.09|phi'(0)|/C
+ * the strong-Wolfe curvature test |phi'(alpha)| <= 0.9|phi'(0)| - part of every acceptance test - cannot pass.  The
+ * kernel ends DCSRCH (bracket set) and _zoom (a_lo <= a_hi) as soon as their bracket lies inside [0, a_safe].  With the
+ * check enabled the oracle keeps replaying every search in full, as SciPy does, evaluates the same rule on the way, and
+ * counts the searches in which the certificate held and those of them that went on to ACCEPT a step (must stay 0),
+ * plus the trials the kernel does not make. */
+static int shortcut_check_on = 0;
 static long long cert_w1_fired = 0, cert_w1_accept_after = 0, cert_zoom_fired = 0, cert_zoom_accept_after = 0;
 static long long cert_trials_skipped = 0;
-void stm_oracle_tail_check(int enable, long long *out9) {
-    if (out9) {
-        out9[0] = tail_fired; out9[1] = tail_accept_after; out9[2] = tail_third_vector; out9[3] = tail_skipped_trials;
-        out9[4] = cert_w1_fired; out9[5] = cert_w1_accept_after; out9[6] = cert_zoom_fired;
-        out9[7] = cert_zoom_accept_after; out9[8] = cert_trials_skipped;
+void stm_oracle_shortcut_check(int enable, long long *out5) {
+    if (out5) {
+        out5[0] = cert_w1_fired; out5[1] = cert_w1_accept_after; out5[2] = cert_zoom_fired;
+        out5[3] = cert_zoom_accept_after; out5[4] = cert_trials_skipped;
     }
-    tail_check_on = enable;
-    tail_fired = tail_accept_after = tail_third_vector = tail_skipped_trials = 0;
+    shortcut_check_on = enable;
     cert_w1_fired = cert_w1_accept_after = cert_zoom_fired = cert_zoom_accept_after = cert_trials_skipped = 0;
 }
 
@@ -318,8 +311,7 @@ static int search_wolfe1(line_t *L, double phi0, double old_phi0, double derphi0
     double width = stpmax - stpmin, width1 = width / 0.5;
     double stx = 0.0, fx = finit, gx = ginit, sty = 0.0, fy = finit, gy = ginit;
     double stmin = 0, stmax = stp + 4.0 * stp;
-    int fired = 0, certw = 0;
-    double *ends = NULL; /* tail check: the two end vectors of the bracket when the rule fired */
+    int certw = 0;
 
     /* DCSRCH.__call__: for i in range(maxiter=100); i = 0 was START */
     for (int it = 0; it < 100; ++it) {
@@ -335,11 +327,9 @@ static int search_wolfe1(line_t *L, double phi0, double old_phi0, double derphi0
             if (f <= ftest && fabs(g) <= gtol * -ginit) conv = 1;
             if (conv) {
                 if (certw) __sync_fetch_and_add(&cert_w1_accept_after, 1);
-                if (fired) __sync_fetch_and_add(&tail_accept_after, 1);
-                free(ends);
                 *alpha = stp; *phi1_out = f; return isfinite(stp) ? 1 : 0;
             }
-            if (warn) { free(ends); return 0; }
+            if (warn) return 0;
 
             if (stage == 1 && f <= fx && f > ftest) {
                 double fm = f - stp * gtest, fxm = fx - stx * gtest, fym = fy - sty * gtest;
@@ -366,48 +356,17 @@ static int search_wolfe1(line_t *L, double phi0, double old_phi0, double derphi0
             if ((brackt && (stp <= stmin || stp >= stmax)) ||
                 (brackt && stmax - stmin <= xtol * stmax))
                 stp = stx;
-            if (tail_check_on && brackt && !certw && L->a_safe > 0.0 && stmax <= L->a_safe) {
+            if (shortcut_check_on && brackt && !certw && L->a_safe > 0.0 && stmax <= L->a_safe) {
                 certw = 1;
                 __sync_fetch_and_add(&cert_w1_fired, 1);
             }
-            if (tail_check_on && brackt && !fired) {
-                const int n = L->p->K1;
-                double *e2 = (double *)malloc(sizeof(double) * 3 * (size_t)n), *gg = e2 + 2 * n;
-                int nd = 0;
-                for (int i = 0; i < n; ++i) {
-                    e2[i] = L->xk[i] + stmin * L->pk[i];
-                    e2[n + i] = L->xk[i] + stmax * L->pk[i];
-                    nd += !(e2[i] == e2[n + i]);
-                }
-                int never = nd <= 1;
-                for (int e = 0; never && e < (nd ? 2 : 1); ++e) {
-                    const double fp = obj_f(L->p, e2 + e * n);
-                    obj_df(L->p, e2 + e * n, gg);
-                    double gd = 0.0;
-                    for (int i = 0; i < n; ++i) gd += gg[i] * L->pk[i];
-                    never = !(fabs(gd) <= gtol * -ginit) || !(fp <= finit + stmin * gtest);
-                }
-                if (never) { fired = 1; ends = e2; __sync_fetch_and_add(&tail_fired, 1); }
-                else free(e2);
-            }
         }
-        if (!isfinite(stp)) { free(ends); return 0; }
-        if (fired) {
-            const int n = L->p->K1;
-            int third = 0;
-            for (int i = 0; i < n && !third; ++i) {
-                const double xi = L->xk[i] + stp * L->pk[i];
-                third = !(xi == ends[i]) && !(xi == ends[n + i]);
-            }
-            if (third) __sync_fetch_and_add(&tail_third_vector, 1);
-            __sync_fetch_and_add(&tail_skipped_trials, 1);
-        }
+        if (!isfinite(stp)) return 0;
         if (certw) __sync_fetch_and_add(&cert_trials_skipped, 1);
         /* task == FG */
         f = ls_phi(L, stp);
         g = ls_derphi(L, stp);
     }
-    free(ends);
     return 0; /* maxiter reached */
 }
 
@@ -450,8 +409,7 @@ static int zoom(line_t *L, double a_lo, double a_hi, double phi_lo, double phi_h
     double a_j = NAN;
     int certz = 0;
     for (;;) {
-        if (tail_check_on && !certz && L->a_safe > 0.0 && a_lo <= L->a_safe && a_hi <= L->a_safe &&
-            a_lo >= 0.0 && a_hi >= 0.0) {
+        if (shortcut_check_on && !certz && L->a_safe > 0.0 && a_lo >= 0.0 && a_lo <= a_hi && a_hi <= L->a_safe) {
             certz = 1;
             __sync_fetch_and_add(&cert_zoom_fired, 1);
         }
@@ -559,7 +517,7 @@ static int bfgs(doc_t *p, double *x, double *work /* 6*n + 3*n*n */, double *fun
         for (int i = 0; i < n; ++i) derphi0 += gfk[i] * pk[i];
 
         L.a_safe = 0.0;
-        if (tail_check_on) {
+        if (shortcut_check_on) {
             /* the kernel's formula and guard (estep_kernel.cuh, "curvature certificate"): bound (i) on the variance
              * term, and bound (ii) from theta at x */
             double pSp = 0.0, mx = 0.0, sm = 0.0, noise = 0.0, hi = 0.0, lo = 0.0, xm = 0.0;

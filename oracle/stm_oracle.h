@@ -60,12 +60,11 @@ int stm_oracle_bfgs(int K, int n, const double *beta_doc, const double *count,
                     const double *mu, const double *siginv, double *x,
                     double *fun, int *nit, int *nfev, int *njev);
 
-/* Self-check of the CUDA kernel's two line-search shortcuts (see stm_oracle.c): returns the counters of the checks made
- * since the last call in out9 = {DCSRCH tail rule: searches in which it fired, of those: a step accepted afterwards, a
- * third trial vector evaluated afterwards, trials it would have skipped; curvature certificate: DCSRCH searches in which
- * it held, of those accepted afterwards, _zoom calls in which it held, of those accepted afterwards, trials it would
- * have skipped}, then enables / disables the check and zeroes the counters.  Off by default. */
-void stm_oracle_tail_check(int enable, long long *out9);
+/* Self-check of the CUDA kernel's line-search shortcut, the curvature certificate (see stm_oracle.c): returns the
+ * counters of the checks made since the last call in out5 = {DCSRCH searches in which the certificate held, of those:
+ * a step accepted afterwards, _zoom calls in which it held, of those accepted afterwards, trials the kernel does not
+ * make}, then enables / disables the check and zeroes the counters.  Off by default. */
+void stm_oracle_shortcut_check(int enable, long long *out5);
 
 #ifdef __cplusplus
 }

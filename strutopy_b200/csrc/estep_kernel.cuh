@@ -68,9 +68,6 @@
 #ifndef STM_CURV_CERT
 #define STM_CURV_CERT 1       // 1: end a line search whose bracket lies where the curvature condition provably cannot hold (see
 #endif                        //    the comment at "curvature certificate" in kernel A)
-#ifndef STM_W1_TAIL_SKIP
-#define STM_W1_TAIL_SKIP 1    // 1: leave a DCSRCH search whose bracket has collapsed onto memoised points that can never be accepted
-#endif                        //    (exact: see the comment at the use; r02: kernel A 28.4 -> ... ms)
 #define STM_BFGS_MAX_THREADS 384   // launch bound of kernel A (register budget = 65536 / this): 12 warps x 160 registers, no spills (r01 A/B: 448 -> 384: 31.3 -> 29.3 ms)
 #endif
 #define STM_PRAGMA2_(x) _Pragma(#x)
@@ -807,7 +804,6 @@ __global__ void __launch_bounds__(STM_BFGS_MAX_THREADS, 1) bfgs_kernel(const Est
         while (!done) {
             // ---------------- evaluate f, g at x + alpha p --------------------------------------
             STM_T(t_ev0);
-            bool memo_hit = false;
             {
                 double xn[KPL];
                 bool same0 = have_cache, same1 = have_cache2;
@@ -823,9 +819,8 @@ __global__ void __launch_bounds__(STM_BFGS_MAX_THREADS, 1) bfgs_kernel(const Est
                 // a collapsing dcsrch interval (~20 % of all evaluations).
                 const bool hit0 = __all_sync(STM_FULL, same0);
                 const bool hit1 = !hit0 && __all_sync(STM_FULL, same1);
-                memo_hit = hit0 || hit1;
 #if STM_DBG_TIMING
-                dbg_t[14] += 1; dbg_t[15] += memo_hit ? 1 : 0;   // slots 14 / 15: steps, memo hits
+                dbg_t[14] += 1; dbg_t[15] += (hit0 || hit1) ? 1 : 0;   // slots 14 / 15: steps, memo hits
 #endif
                 if (hit1) {
 #pragma unroll
@@ -1100,45 +1095,6 @@ __global__ void __launch_bounds__(STM_BFGS_MAX_THREADS, 1) bfgs_kernel(const Est
                         stp = S.stx;
                     S.w1_it++;
                     bool dead = false;
-#if STM_W1_TAIL_SKIP
-                    // The tail of a failing search.  Near convergence the steps are so small against x that the
-                    // whole bracket [stmin, stmax] maps onto one or two neighbouring trial vectors x + stp p, both
-                    // memoised, and DCSRCH spends its remaining (up to 100) iterations alternating between them
-                    // until xtol or maxiter ends it with stp = None (-> Wolfe-2).  That outcome is known as soon as
-                    //  (1) the vectors at the two ends of the bracket differ in at most ONE component: every later
-                    //      trial lies in the bracket (_dcsrch.py:472-500 keeps stp in [stmin, stmax], the bracket only
-                    //      shrinks) and fl(x_i + fl(stp p_i)) is monotone in stp, so every later trial vector is one
-                    //      of those two;
-                    //  (2) both are memoised with their phi and phi', and neither can pass the convergence test
-                    //      (_dcsrch.py:373: f <= finit + stp gtest and |g| <= gtol |ginit|) for ANY stp of the bracket:
-                    //      |phi'| fails, or phi is above the test line at stmin (gtest < 0: the line only falls).
-                    // No further evaluation would be fresh, no trial accepted, and nothing of the DCSRCH state
-                    // outlives the search: going to Wolfe-2 now is what the replay arrives at.  On the C oracle
-                    // (D=3000 of the C3 workload) this removes 64 % of the memo-hit steps and never fires before an
-                    // acceptance (0 of 2593 searches).
-                    if (memo_hit && S.brackt && have_cache2 && dphi_ok && dphi2_ok) {
-                        bool a0 = true, a1 = true, b0 = true, b1 = true;
-                        int nd_l = 0;
-#pragma unroll
-                        for (int i = 0; i < KPL; ++i) {
-                            const double xa = __dadd_rn(x[i], __dmul_rn(S.stmin, p[i]));
-                            const double xb = __dadd_rn(x[i], __dmul_rn(S.stmax, p[i]));
-                            a0 = a0 && (xa == xt[i]); a1 = a1 && (xa == xt2[i]);
-                            b0 = b0 && (xb == xt[i]); b1 = b1 && (xb == xt2[i]);
-                            nd_l += !(xa == xb);
-                        }
-                        const bool A0 = __all_sync(STM_FULL, a0), A1 = __all_sync(STM_FULL, a1);
-                        const bool B0 = __all_sync(STM_FULL, b0), B1 = __all_sync(STM_FULL, b1);
-                        const int nd = __reduce_add_sync(STM_FULL, nd_l);
-                        if (nd <= 1 && (A0 || A1) && (B0 || B1)) {
-                            const double top = S.finit + S.stmin * S.gtest, gmax = c2 * -S.ginit;
-                            const bool never0 = !(fabs(dphi) <= gmax) || !(f_eval <= top);
-                            const bool never1 = !(fabs(dphi2) <= gmax) || !(S.f2 <= top);
-                            const bool use0 = A0 || B0, use1 = (A1 && !A0) || (B1 && !B0);
-                            dead = (!use0 || never0) && (!use1 || never1);
-                        }
-                    }
-#endif
 #if STM_CURV_CERT
                     if (S.brackt && S.a_safe > 0.0 && S.stmax <= S.a_safe) dead = true;   // curvature certificate: cannot converge any more
 #endif
@@ -1203,11 +1159,12 @@ __global__ void __launch_bounds__(STM_BFGS_MAX_THREADS, 1) bfgs_kernel(const Est
                 ls = LS_ZOOM;
             }
 #if STM_CURV_CERT
-            // curvature certificate: _zoom's trials stay inside [a_lo, a_hi] (cubic / quadratic steps are range-checked,
-            // else bisection), the interval only shrinks, and no step in it can be accepted: _zoom will run out of
-            // iterations and return None
-            if (ls == LS_ZOOM && !accept && !fail && S.a_safe > 0.0 && S.a_lo <= S.a_safe && S.a_hi <= S.a_safe &&
-                S.a_lo >= 0.0 && S.a_hi >= 0.0)
+            // curvature certificate: with a_lo <= a_hi _zoom's trials stay inside [a_lo, a_hi] (cubic / quadratic steps
+            // are range-checked against margins of delta * (a_hi - a_lo) >= 0, else bisection — for a_hi < a_lo those
+            // margins are negative and a trial may leave the interval, so that case is left to the replay), every
+            // trial has phi' < 0, which keeps a_lo <= a_hi in both update branches (_linesearch.py:611-627), the
+            // interval only shrinks, and no step in it can be accepted: _zoom runs out of iterations and returns None
+            if (ls == LS_ZOOM && !accept && !fail && S.a_safe > 0.0 && S.a_lo >= 0.0 && S.a_lo <= S.a_hi && S.a_hi <= S.a_safe)
                 fail = 1;
 #endif
             if (ls == LS_ZOOM && !accept && !fail) {
@@ -1349,7 +1306,7 @@ __global__ void __launch_bounds__(STM_BFGS_MAX_THREADS, 1) bfgs_kernel(const Est
                     // brackt set; _zoom always), no later trial can be accepted and the search is known to fail —
                     // which is all that is left of it: a failed DCSRCH hands nothing to Wolfe-2, a failed _zoom raises
                     // _LineSearchError and BFGS returns the current x (_optimize.py:1446-1449).  The C oracle replays
-                    // every search in full and checks this rule on the way (stm_oracle_tail_check): 0 acceptances
+                    // every search in full and checks this rule on the way (stm_oracle_shortcut_check): 0 acceptances
                     // after the certificate in every state of tests/ and tools/.
                     {
                         const bool th_ok = (ex_owner == 0);   // ex[], scale_e describe theta at x

@@ -514,8 +514,7 @@ def test_doc_bound_and_repair_vs_numpy_port_true_eigenvalues(lib):
 
 
 def test_line_search_shortcuts_keep_every_outcome():
-    """Kernel A does not replay line searches whose failure is already decided (curvature certificate + DCSRCH tail
-    rule).  Against the C oracle, which replays every search in full as SciPy does: status, iteration count,
+    """Kernel A does not replay line searches whose failure is already decided (curvature certificate).  Against the C oracle, which replays every search in full as SciPy does: status, iteration count,
     repair stage EQUAL for every document, eta and the per-document bounds at the usual tolerances — while the device
     makes a fraction of the oracle's objective evaluations (the shortcut is what runs, not a dormant branch).  K=50
     spectral-init states of EM iterations 0-2 and config 2's K=20 random-init states."""
