@@ -233,6 +233,17 @@ def test_line_search_shortcut_is_exact_on_the_oracle():
         assert cnts["cert_w1_accept_after"] == 0 and cnts["cert_zoom_accept_after"] == 0, (name, cnts)
         for k in ("eta", "doc_bound", "status", "nit", "nfev", "njev"):
             np.testing.assert_array_equal(plain[k], checked[k])
+    # content aspects (A = 2): the live reference's own state, per-document status / iteration counts pinned by the fixture
+    g = load_golden("estep_content.npz")
+    c_oracle.shortcut_check(True)
+    try:
+        r = c_oracle.estep(g["doc_ptr"], g["word_id"], g["count"].astype(np.float64), g["it0_beta"], g["it0_mu"],
+                           g["it0_siginv"], float(g["it0_sigmaentropy"]), g["it0_eta0"], aspect=g["aspect"], nthreads=2)
+    finally:
+        cnts = c_oracle.shortcut_check(False)
+    np.testing.assert_array_equal(r["status"], g["it0_status"])
+    np.testing.assert_array_equal(r["nit"], g["it0_nit"])
+    assert cnts["cert_w1_fired"] > 0 and cnts["cert_w1_accept_after"] == 0 and cnts["cert_zoom_accept_after"] == 0, cnts
 
 
 def test_em_toy_ctm_trace_c_oracle():
