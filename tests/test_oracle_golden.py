@@ -246,6 +246,55 @@ def test_line_search_shortcut_is_exact_on_the_oracle():
     assert cnts["cert_w1_fired"] > 0 and cnts["cert_w1_accept_after"] == 0 and cnts["cert_zoom_accept_after"] == 0, cnts
 
 
+def test_curvature_bounds_behind_the_certificate():
+    """The two inequalities the kernel's curvature certificate rests on, checked numerically in extended
+    precision on random instances of the reference's gradient g(eta) = S (eta - mu) - a + N softmax([eta, 0]) (stm.py:
+    946-958): phi'(alpha) = g(x + alpha p) . p is non-decreasing, and
+        phi'(alpha) - phi'(0) <= alpha (p'Sp + N min(max pt^2, |p|^2 / 2))                       for every alpha >= 0,
+        phi'(alpha) - phi'(0) <= alpha (p'Sp + 1.11 N Var_theta(x)(pt))   while alpha (max pt - min pt) <= 0.1,
+    pt = [p, 0]."""
+    rng = np.random.default_rng(7)
+    ld = np.longdouble
+    worst = 0.0
+    for trial in range(400):
+        K1 = int(rng.integers(1, 60))
+        scale = 10.0 ** rng.uniform(-3, 1.5)
+        x = (rng.normal(size=K1) * rng.uniform(0.1, 6)).astype(ld)
+        mu = rng.normal(size=K1).astype(ld)
+        Sd = (10.0 ** rng.uniform(-2, 2, size=K1)).astype(ld)
+        a = (rng.gamma(1.0, 5.0, size=K1)).astype(ld)
+        N = ld(rng.integers(1, 400))
+        p = (rng.normal(size=K1) * scale).astype(ld)
+        if trial % 3 == 0:
+            p[rng.integers(0, K1)] *= 50          # one dominant component
+
+        def dphi(al):
+            e = np.exp(np.append(x + al * p, ld(0)) - np.max(np.append(x + al * p, ld(0))))
+            th = e / e.sum()
+            g = Sd * (x + al * p - mu) - a + N * th[:K1]
+            return float((g * p).sum()), th
+
+        d0, th0 = dphi(ld(0))
+        pt = np.append(p, ld(0))
+        pSp = float((Sd * p * p).sum())
+        C1 = pSp + float(N) * min(float((pt * pt).max()), 0.5 * float((p * p).sum()))
+        m1 = float((th0 * pt).sum())
+        V0 = float((th0 * (pt - m1) ** 2).sum())
+        C2 = pSp + 1.11 * float(N) * V0
+        R = float(pt.max() - pt.min())
+        prev = d0
+        for al in np.concatenate([np.geomspace(1e-6, 1.0, 25) * (0.1 / max(R, 1e-12)), np.geomspace(1e-4, 30, 25)]):
+            d, _ = dphi(ld(al))
+            tol = 1e-13 * (abs(d0) + abs(d) + al * C1)
+            assert d >= prev - tol or al < prev_al, (trial, al)      # monotone along each increasing sweep
+            assert d - d0 <= al * C1 + tol, (trial, al, d - d0, al * C1)
+            if al * R <= 0.1:
+                assert d - d0 <= al * C2 + tol, (trial, al, d - d0, al * C2)
+                worst = max(worst, (d - d0) / max(al * C2, 1e-300))
+            prev, prev_al = d, al
+    assert 0.5 < worst <= 1.0 + 1e-9, worst      # bound (ii) is tight (the certificate gives little away), never violated
+
+
 def test_em_toy_ctm_trace_c_oracle():
     g = load_golden("em_toy_ctm.npz")
     run = lambda *a, **k: c_oracle.estep(*a, **k)
