@@ -1300,7 +1300,7 @@ __global__ void __launch_bounds__(STM_BFGS_MAX_THREADS, 1) bfgs_kernel(const Est
                     // |phi'(alpha)| <= 0.9 |phi'(0)| (_dcsrch.py:373, _linesearch.py:433, :606).  For alpha <= a_safe =
                     // 0.09 |phi'(0)| / C (C from (i), or from (ii) with a_safe R <= 0.1) the exact phi'(alpha) lies in
                     // [phi'(0), 0.91 phi'(0)], so the test fails by a margin of 0.01 |phi'(0)|.  The guard below bounds the
-                    // rounding error of ANY fp64 evaluation of g . p by 1e-12 sum_i |p_i| (|S (x-mu)|_i + |a_i| + N) — four
+                    // rounding error of ANY fp64 evaluation of g . p by 1e-12 sum_i |p_i| (|S (x-mu)|_i + |a_i| + N) — three
                     // orders above the real thing — and gives no certificate (a_safe = 0) unless that is below the margin.
                     // Consequence: once a search's bracket lies inside [0, a_safe] and can only shrink (DCSRCH with
                     // brackt set; _zoom always), no later trial can be accepted and the search is known to fail —
