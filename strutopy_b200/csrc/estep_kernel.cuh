@@ -455,6 +455,17 @@ __device__ __forceinline__ void tm_ld4(uint32_t taddr, uint32_t (&v)[4]) {
 __device__ __forceinline__ void tm_ld2(uint32_t taddr, uint32_t (&v)[2]) {
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x2.b32 {%0,%1}, [%2];" : "=r"(v[0]), "=r"(v[1]) : "r"(taddr) : "memory");
 }
+// four doubles of this lane <-> 8 consecutive 32-bit columns of its tensor-memory lane
+__device__ __forceinline__ void tm_st_d4(uint32_t taddr, double a, double b, double c, double d) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"r"(taddr),
+                 "r"(__double2loint(a)), "r"(__double2hiint(a)), "r"(__double2loint(b)), "r"(__double2hiint(b)),
+                 "r"(__double2loint(c)), "r"(__double2hiint(c)), "r"(__double2loint(d)), "r"(__double2hiint(d))
+                 : "memory");
+}
+__device__ __forceinline__ void tm_d4_from(const uint32_t (&v)[8], double& a, double& b, double& c, double& d) {
+    a = __hiloint2double((int)v[1], (int)v[0]); b = __hiloint2double((int)v[3], (int)v[2]);
+    c = __hiloint2double((int)v[5], (int)v[4]); d = __hiloint2double((int)v[7], (int)v[6]);
+}
 __device__ __forceinline__ void tm_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tm_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 // beta_f2d on raw bits (what tcgen05.ld returns)
@@ -1795,6 +1806,9 @@ constexpr int POST_GT = POST_GW * 32;
 __host__ __device__ constexpr int post_ust(int GW) {        // stride of the small fp64 vectors (Dg, u, d): >= 4 nb4
     return GW == 3 ? 56 : (GW == 5 ? 72 : (GW <= 11 ? 104 : 136));
 }
+#ifndef STM_POST_TMEM
+#define STM_POST_TMEM 1      // kernel B, K <= 64: the Hessian data term waits in TENSOR MEMORY (not in the L2 scratch) for the tile to die
+#endif
 #ifndef STM_ASM_BATCH
 #define STM_ASM_BATCH 2      // (r02 A/B at C3 with stepped indices: 1 / 2 / 4 -> 8.34 / 8.32 / 8.37 ms) Hessian elements per thread whose L2 loads are in flight together (kernel B assembly)
 #endif
@@ -1978,8 +1992,25 @@ __global__ void __launch_bounds__(post_group_max_threads(GW), post_group_min_blo
         __syncthreads();
     }
 
+    // K <= 64: the DMMA accumulators of a warp's row passes wait in tensor memory (96 columns of the warp's own 32
+    // lanes: 3 passes x 8 blocks x 2 doubles) until every warp of the group is done with the tile and H can be written
+    // over it — kernel B has no other use for the 256 KB, and the L2 round trip of a bounce buffer was 17 % of its
+    // stall samples.  One CTA per SM (registers), <= 20 warps: 5 x 96 columns per lane quadrant.
+    constexpr bool USE_TM = (STM_POST_TMEM != 0) && NBMAX <= 8;
+    __shared__ uint32_t tm_base_b;
+    if constexpr (USE_TM) {
+        if (warp_u == 0) {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(&tm_base_b)));
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;");
+        __syncthreads();
+        asm volatile("tcgen05.fence::after_thread_sync;");
+    }
+    const uint32_t tmw = USE_TM ? tm_base_b + ((uint32_t)((warp_u & 3) * 32) << 16) + (uint32_t)((warp_u >> 2) * 96) : 0u;
+
     const int ggrp = blockIdx.x * (blockDim.x / POST_GT) + grp;
-    double* Hg = P.scratch + (size_t)ggrp * P.scratch_stride + (size_t)K1 * K1;   // Hessian bounce (L2)
+    double* Hg = P.scratch + (size_t)ggrp * P.scratch_stride + (size_t)K1 * K1;   // Hessian bounce (L2; K > 64 only)
     double* sig_acc = P.sigma_ss_rep + (size_t)(ggrp % P.n_rep) * K1 * K1;
 
     // this thread's 4x4 patch of the lower triangle
@@ -2151,7 +2182,7 @@ __global__ void __launch_bounds__(post_group_max_threads(GW), post_group_min_blo
                     }
                 }
             } else {
-            int qpos = 0;
+            int qpos = 0, ps = 0;
 #pragma unroll 1
             for (int br = nbp - 1; br >= 0; --br, ++qpos) {
                 const int m6 = qpos % (2 * POST_GW);
@@ -2183,14 +2214,21 @@ __global__ void __launch_bounds__(post_group_max_threads(GW), post_group_min_blo
                     }
                 }
                 // C fragment: row = lane>>2, cols = 2*(lane&3) + {0,1}
-                const int gi = br * 8 + kk;
+                if constexpr (USE_TM) {
 #pragma unroll
-                for (int bc = 0; bc < NBMAX; ++bc) {
-                    if (bc <= br) {
+                    for (int bc = 0; bc < NBMAX; bc += 2)
+                        tm_st_d4(tmw + (uint32_t)(ps * 4 * NBMAX + 4 * bc), acc[bc][0], acc[bc][1], acc[bc + 1][0], acc[bc + 1][1]);
+                    ++ps;
+                } else {
+                    const int gi = br * 8 + kk;
 #pragma unroll
-                        for (int c = 0; c < 2; ++c) {
-                            const int gj = bc * 8 + 2 * w4 + c;
-                            if (gi < K1 && gj <= gi) Hg[(size_t)gi * K1 + gj] = acc[bc][c];
+                    for (int bc = 0; bc < NBMAX; ++bc) {
+                        if (bc <= br) {
+#pragma unroll
+                            for (int c = 0; c < 2; ++c) {
+                                const int gj = bc * 8 + 2 * w4 + c;
+                                if (gi < K1 && gj <= gi) Hg[(size_t)gi * K1 + gj] = acc[bc][c];
+                            }
                         }
                     }
                 }
@@ -2200,13 +2238,57 @@ __global__ void __launch_bounds__(post_group_max_threads(GW), post_group_min_blo
             }
         }
             }
+        if constexpr (USE_TM) tm_wait_st();
         group_bar<GW>(grp);   // tile dead; Hg and v3 complete
 
         // ---- assemble H = data - N theta theta' + diag(-rowsum + N theta) + siginv (stm.py:1007-1015)
         // (the data term comes back from the L2 bounce.  The threads walk the packed lower triangle, element gt, gt + GT,
         // ...: (row, column) is stepped forward by GT elements per visit — no square root per element — and the loads
         // of STM_ASM_BATCH visits are issued together so that one L2 round trip covers them)
-        {
+        if constexpr (USE_TM) {
+            // every warp takes its own row passes back out of tensor memory and assembles their elements
+            const int nbp = (K + 7) >> 3;
+            const int w4 = lane & 3, kk = lane >> 2;
+            int qpos = 0, ps = 0;
+#pragma unroll 1
+            for (int br = nbp - 1; br >= 0; --br, ++qpos) {
+                const int m6 = qpos % (2 * POST_GW);
+                if ((m6 < POST_GW ? m6 : 2 * POST_GW - 1 - m6) != wg) continue;
+                uint32_t raw[NBMAX / 2][8];
+#pragma unroll
+                for (int b2 = 0; b2 < NBMAX / 2; ++b2) tm_ld8(tmw + (uint32_t)(ps * 4 * NBMAX + 8 * b2), raw[b2]);
+                tm_wait_ld();
+                ++ps;
+                double acc[NBMAX][2];
+#pragma unroll
+                for (int b2 = 0; b2 < NBMAX / 2; ++b2)
+                    tm_d4_from(raw[b2], acc[2 * b2][0], acc[2 * b2][1], acc[2 * b2 + 1][0], acc[2 * b2 + 1][1]);
+                const int gi = br * 8 + kk;
+                if (gi < K1) {
+                    const double thr = v2[gi];
+#pragma unroll
+                    for (int bc = 0; bc < NBMAX; ++bc) {
+                        if (bc <= br) {
+#pragma unroll
+                            for (int c = 0; c < 2; ++c) {
+                                const int gj = bc * 8 + 2 * w4 + c;
+                                if (gj <= gi) {
+                                    const double thk = v2[gj];
+                                    double h = acc[bc][c] - Nsum * (thr * thk);
+                                    if (gj == gi) {
+                                        h = (h - v3[gj] + Nsum * thk) + P.prior[gj];
+                                        Dg[gj] = h;
+                                        if (!(h > 0.0)) red[21] = 1.0;
+                                    }
+                                    Hm[(size_t)gi * HS + gj] = h;
+                                    Hm[(size_t)gj * HS + gi] = h;
+                                }
+                            }
+                        }
+                    }
+                }
+            }
+        } else {
             const int ntri = K1 * (K1 + 1) / 2;
             int r = 0, k = gt;                       // element gt of the packed triangle = (r, k)
             while (k > r) { k -= r + 1; ++r; }
@@ -2364,6 +2446,11 @@ __global__ void __launch_bounds__(post_group_max_threads(GW), post_group_min_blo
                 }
         }
     }  // document loop
+    if constexpr (USE_TM) {
+        asm volatile("tcgen05.fence::before_thread_sync;");
+        __syncthreads();
+        if (warp_u == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tm_base_b));
+    }
 }
 
 }  // namespace stm
