@@ -1806,6 +1806,9 @@ constexpr int POST_GT = POST_GW * 32;
 __host__ __device__ constexpr int post_ust(int GW) {        // stride of the small fp64 vectors (Dg, u, d): >= 4 nb4
     return GW == 3 ? 56 : (GW == 5 ? 72 : (GW <= 11 ? 104 : 136));
 }
+#ifndef STM_HESS_FUSED
+#define STM_HESS_FUSED 1     // kernel B, K = 49..56: a warp's block rows of the DMMA Hessian pass fused into one pass over the words
+#endif
 #ifndef STM_POST_TMEM
 #define STM_POST_TMEM 1      // kernel B, K <= 64: the Hessian data term waits in TENSOR MEMORY (not in the L2 scratch) for the tile to die
 #endif
@@ -1874,6 +1877,71 @@ STM_PRAGMA_(unroll STM_HESS_UNROLL)
             asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
                          : "+d"(acc[t][0]), "+d"(acc[t][1])
                          : "d"(fa), "d"(fr[t]));
+    }
+}
+
+// K = 49 .. 56 with three warps per document (the benchmark shape): a warp's two or three block rows (R0 > R1 > R2,
+// -1 = none) in ONE pass over the words.  The B fragments fr[0 .. R0] are formed once per word quadruple and serve all
+// of the warp's rows (separate passes form sum (R + 2) of them); every element sees the same operations in the same
+// order as in hess_row_pass, so the sums are bit-identical.
+template <int R0, int R1, int R2>
+__device__ __forceinline__ void hess_rows_fused(const float* tile, int TS, int n, const double* wv, const double* wv2,
+                                                const int* wid, const double (&ek)[8], int K, double* beta_ss_a, int w4,
+                                                int kk, double (&acc0)[8][2], double (&acc1)[8][2],
+                                                double (&acc2)[8][2], double& rs0, double& rs1, double& rs2) {
+    const bool ok0 = 8 * R0 + kk < K, ok1 = R1 >= 0 && 8 * R1 + kk < K, ok2 = R2 >= 0 && 8 * R2 + kk < K;
+    double* s0 = beta_ss_a + 8 * R0 + kk;
+    double* s1 = beta_ss_a + 8 * (R1 < 0 ? 0 : R1) + kk;
+    double* s2 = beta_ss_a + 8 * (R2 < 0 ? 0 : R2) + kk;
+#pragma unroll 1
+    for (int vb = 0; vb < n; vb += 4) {
+        const int v = vb + w4;
+        const double sc = wv[v];                      // zero for the (< 4) slots past the last word
+        const float* tb = tile + (size_t)min(v, n - 1) * TS + kk;
+        double fr[R0 + 1];
+#pragma unroll
+        for (int t = 0; t <= R0; ++t) fr[t] = beta_f2d(tb[8 * t]) * ek[t];
+        const bool vin = v < n;
+        const double sc2 = sc * sc;
+        {
+            const double fa = fr[R0] * sc2;
+            if (vin && ok0) {
+                const double ph = fr[R0] * (sc * wv2[v]);
+                rs0 += ph;
+                if (!STM_DBG_NO_PHI) red_add_f64(s0 + wid[v], ph);
+            }
+#pragma unroll
+            for (int t = 0; t <= R0; ++t)
+                asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                             : "+d"(acc0[t][0]), "+d"(acc0[t][1])
+                             : "d"(fa), "d"(fr[t]));
+        }
+        if constexpr (R1 >= 0) {
+            const double fa = fr[R1] * sc2;
+            if (vin && ok1) {
+                const double ph = fr[R1] * (sc * wv2[v]);
+                rs1 += ph;
+                if (!STM_DBG_NO_PHI) red_add_f64(s1 + wid[v], ph);
+            }
+#pragma unroll
+            for (int t = 0; t <= R1; ++t)
+                asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                             : "+d"(acc1[t][0]), "+d"(acc1[t][1])
+                             : "d"(fa), "d"(fr[t]));
+        }
+        if constexpr (R2 >= 0) {
+            const double fa = fr[R2] * sc2;
+            if (vin && ok2) {
+                const double ph = fr[R2] * (sc * wv2[v]);
+                rs2 += ph;
+                if (!STM_DBG_NO_PHI) red_add_f64(s2 + wid[v], ph);
+            }
+#pragma unroll
+            for (int t = 0; t <= R2; ++t)
+                asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                             : "+d"(acc2[t][0]), "+d"(acc2[t][1])
+                             : "d"(fa), "d"(fr[t]));
+        }
     }
 }
 
@@ -2179,6 +2247,42 @@ __global__ void __launch_bounds__(post_group_max_threads(GW), post_group_min_blo
                         rs += __shfl_xor_sync(STM_FULL, rs, 1);
                         rs += __shfl_xor_sync(STM_FULL, rs, 2);
                         if (w4 == 0 && kb < KV) v3[kb] = rs;
+                    }
+                }
+            } else if (STM_HESS_FUSED && USE_TM && NBMAX == 8 && POST_GW == 3 && nbp == 7) {
+                if constexpr (NBMAX == 8 && POST_GW == 3) {
+                    double acc0[8][2], acc1[8][2], acc2[8][2];
+#pragma unroll
+                    for (int bc = 0; bc < 8; ++bc) {
+                        acc0[bc][0] = 0.0; acc0[bc][1] = 0.0; acc1[bc][0] = 0.0; acc1[bc][1] = 0.0;
+                        acc2[bc][0] = 0.0; acc2[bc][1] = 0.0;
+                    }
+                    double rs0 = 0.0, rs1 = 0.0, rs2 = 0.0;
+                    int r0, r1, r2;      // the snake deal of block rows 6 .. 0 over three warps: {6,1,0} {5,2} {4,3}
+                    if (wg == 0) {
+                        hess_rows_fused<6, 1, 0>(tile, TS, n, wv, wv2, wid, ek, K, beta_ss_a, w4, kk, acc0, acc1, acc2, rs0, rs1, rs2);
+                        r0 = 6; r1 = 1; r2 = 0;
+                    } else if (wg == 1) {
+                        hess_rows_fused<5, 2, -1>(tile, TS, n, wv, wv2, wid, ek, K, beta_ss_a, w4, kk, acc0, acc1, acc2, rs0, rs1, rs2);
+                        r0 = 5; r1 = 2; r2 = -1;
+                    } else {
+                        hess_rows_fused<4, 3, -1>(tile, TS, n, wv, wv2, wid, ek, K, beta_ss_a, w4, kk, acc0, acc1, acc2, rs0, rs1, rs2);
+                        r0 = 4; r1 = 3; r2 = -1;
+                    }
+                    // the same three tensor-memory slots, in the order the assembly below walks the warp's rows
+#pragma unroll
+                    for (int bc = 0; bc < 8; bc += 2) {
+                        tm_st_d4(tmw + (uint32_t)(4 * bc), acc0[bc][0], acc0[bc][1], acc0[bc + 1][0], acc0[bc + 1][1]);
+                        tm_st_d4(tmw + (uint32_t)(32 + 4 * bc), acc1[bc][0], acc1[bc][1], acc1[bc + 1][0], acc1[bc + 1][1]);
+                        tm_st_d4(tmw + (uint32_t)(64 + 4 * bc), acc2[bc][0], acc2[bc][1], acc2[bc + 1][0], acc2[bc + 1][1]);
+                    }
+                    rs0 += __shfl_xor_sync(STM_FULL, rs0, 1); rs0 += __shfl_xor_sync(STM_FULL, rs0, 2);
+                    rs1 += __shfl_xor_sync(STM_FULL, rs1, 1); rs1 += __shfl_xor_sync(STM_FULL, rs1, 2);
+                    rs2 += __shfl_xor_sync(STM_FULL, rs2, 1); rs2 += __shfl_xor_sync(STM_FULL, rs2, 2);
+                    if (w4 == 0) {
+                        v3[8 * r0 + kk] = rs0;
+                        if (r1 >= 0) v3[8 * r1 + kk] = rs1;
+                        if (r2 >= 0) v3[8 * r2 + kk] = rs2;
                     }
                 }
             } else {
