@@ -98,10 +98,13 @@ def test_wiki_shipped_known_answer(lib, K):
     np.testing.assert_array_equal(o["repair"], ref["repair"])
 
 
-@pytest.mark.parametrize("D,V,K,nw", [(1500, 1500, 8, 60), (1200, 3000, 33, 150), (600, 2500, 70, 150),
-                                      (400, 2000, 100, 200), (300, 2000, 128, 120)])
+@pytest.mark.parametrize("D,V,K,nw", [(1500, 1500, 8, 60), (1200, 3000, 33, 150), (700, 2500, 54, 150),
+                                      (600, 2500, 60, 150), (600, 2500, 70, 150), (400, 2000, 100, 200),
+                                      (300, 2000, 128, 120)])
 def test_estep_vs_c_oracle_shapes(lib, D, V, K, nw):
-    """every KPL instantiation (K <= 32, 64, 96, 128) and several length classes"""
+    """every KPL instantiation (K <= 32, 64, 96, 128), kernel B's group widths (three warps: K <= 53, five: K <= 64 with
+    the tensor-memory staging, the L2 bounce above; K = 54: the fused row passes with a ragged last topic block) and
+    several length classes"""
     ptr, ids, cnt, X, _ = synthetic_corpus(D, V, K, n_words=nw, seed=K)
     beta = random_init_beta(K, V).astype(np.float32).astype(np.float64)
     rng = np.random.default_rng(K)
