@@ -622,8 +622,9 @@ def ours(args):
                          "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s",
                          "fp64": fp64,
                          "limiter": "kernel A: instruction fetch (gcc__cache_requests_type_instruction at 97 % of its peak "
-                                    "rate, no_instruction the first stall reason); kernel B: fixed-latency dependencies and "
-                                    "named barriers at IPC 1.8 (profiles/r02d_estep_pair_ncu_summary.txt, r02_tuning_log.md)"},
+                                    "rate, no_instruction the first stall reason); kernel B: fixed-latency dependencies, named "
+                                    "barriers and instruction fetch (88 % of that peak) at IPC 1.8 "
+                                    "(profiles/r02d_estep_pair_ncu_summary.txt, r02_tuning_log.md)"},
             "cpu_baseline": cpu,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "api": "stm_estep_host (C ABI, fp64 host buffers in the reference's layouts; corpus resident; "
